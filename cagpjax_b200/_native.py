@@ -1,0 +1,234 @@
+"""ctypes binding of libcagp_b200.so (the C ABI declared in include/cagp_b200.h).
+
+This is the test-time / torch-side binding of the drop-in boundary; a JAX host would bind the
+same symbols as XLA FFI custom calls.  There is NO fallback: if the shared
+library is missing or a tensor is not on a CUDA device the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libcagp_b200.so")
+
+FAMILIES = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+F32, F64 = 0, 1
+
+
+class NativeLibraryError(RuntimeError):
+    """Raised when libcagp_b200.so is missing or a native call fails."""
+
+
+class KernelDesc(Structure):
+    _fields_ = [
+        ("family", c_int32),
+        ("dtype", c_int32),
+        ("n_lengthscale", c_int32),
+        ("reserved", c_int32),
+        ("lengthscale", c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    "cagp_last_error_string": (c_char_p, []),
+    "cagp_version": (c_int, []),
+    "cagp_padded_dim": (c_int, [c_int32]),
+    "cagp_scale_inputs": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
+    "cagp_ks_blocksparse_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                        c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "cagp_ks_bwd_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int64, c_int32, c_int32]),
+    "cagp_ks_blocksparse_bwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                        c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_size_t, c_void_p]),
+    "cagp_project_rows": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "cagp_gram_mtm": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
+    "cagp_assemble_cotangent": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cagp_project_rows_bwd": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cagp_predict_ws_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "cagp_predict_moments": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises NativeLibraryError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise NativeLibraryError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C cagpjax_b200/csrc`). There is no CPU or eager fallback for this path."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().cagp_last_error_string().decode()
+        raise NativeLibraryError(f"{what} failed (status {rc}): {msg}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float64:
+        return F64
+    if dtype == torch.float32:
+        return F32
+    raise TypeError(f"unsupported dtype {dtype}; the native kernels are float32/float64 only")
+
+
+def _ptr(t: torch.Tensor):
+    return c_void_p(t.data_ptr())
+
+
+def _require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if not t.is_cuda:
+            raise NativeLibraryError(
+                "the CaGP hot path runs only on CUDA tensors (sm_100a kernels); got a tensor on "
+                f"{t.device}. There is no CPU fallback."
+            )
+        if not t.is_contiguous():
+            raise ValueError("native kernels need contiguous tensors")
+
+
+def _stream(t: torch.Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def make_desc(family: str, lengthscale: torch.Tensor, dtype: torch.dtype) -> KernelDesc:
+    ls = lengthscale.reshape(-1)
+    return KernelDesc(FAMILIES[family], dtype_code(dtype), ls.numel(), 0, ls.data_ptr())
+
+
+def padded_dim(d: int) -> int:
+    v = load().cagp_padded_dim(d)
+    if v < 0:
+        raise NativeLibraryError(f"input dimension {d} > 32 is not supported by the native kernels")
+    return v
+
+
+def scale_inputs(family: str, X: torch.Tensor, lengthscale: torch.Tensor) -> torch.Tensor:
+    """xs (padded_dim(d), n): scaled, transposed inputs."""
+    _require_cuda(X, lengthscale)
+    n, d = X.shape
+    ls = lengthscale.reshape(-1).to(X.dtype).contiguous()
+    xs = torch.empty((padded_dim(d), n), dtype=X.dtype, device=X.device)
+    kd = make_desc(family, ls, X.dtype)
+    with torch.cuda.device(X.device):
+        _check(load().cagp_scale_inputs(byref(kd), _ptr(X), n, d, _ptr(xs), n, _stream(X)), "cagp_scale_inputs")
+    return xs
+
+
+def ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale) -> torch.Tensor:
+    """Mt (k, m) = (K'(X1, X2) S)^T."""
+    _require_cuda(xs1, xs2, s)
+    m, n = xs1.shape[1], xs2.shape[1]
+    Mt = torch.empty((k, m), dtype=xs1.dtype, device=xs1.device)
+    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    kd = make_desc(family, ls, xs1.dtype)
+    with torch.cuda.device(xs1.device):
+        _check(load().cagp_ks_blocksparse_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Mt), m,
+                                              _stream(xs1)), "cagp_ks_blocksparse_fwd")
+    return Mt
+
+
+def ks_blocksparse_bwd(family, xs1, xs2, d, s, k, Gt, lengthscale):
+    """(s_bar (n), ls_bar (n_lengthscale)) for cotangent Gt (k, m)."""
+    _require_cuda(xs1, xs2, s, Gt)
+    m, n = xs1.shape[1], xs2.shape[1]
+    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    kd = make_desc(family, ls, xs1.dtype)
+    lib = load()
+    ws_bytes = lib.cagp_ks_bwd_ws_bytes(byref(kd), m, n, d, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs1.device)
+    s_bar = torch.empty(n, dtype=xs1.dtype, device=xs1.device)
+    ls_bar = torch.empty(ls.numel(), dtype=xs1.dtype, device=xs1.device)
+    with torch.cuda.device(xs1.device):
+        _check(lib.cagp_ks_blocksparse_bwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Gt),
+                                           Gt.shape[1], _ptr(s_bar), _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)),
+               "cagp_ks_blocksparse_bwd")
+    return s_bar, ls_bar
+
+
+def project_rows(Mt, row_offset, n_total, s_local, yt_local):
+    """A' (k, k) partial over the local rows and c' (k)."""
+    _require_cuda(Mt, s_local, yt_local)
+    k, m = Mt.shape
+    A = torch.empty((k, k), dtype=Mt.dtype, device=Mt.device)
+    c = torch.empty(k, dtype=Mt.dtype, device=Mt.device)
+    with torch.cuda.device(Mt.device):
+        _check(load().cagp_project_rows(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(s_local),
+                                        _ptr(yt_local), _ptr(A), _ptr(c), _stream(Mt)), "cagp_project_rows")
+    return A, c
+
+
+def gram_mtm(Mt):
+    _require_cuda(Mt)
+    k, m = Mt.shape
+    B = torch.empty((k, k), dtype=Mt.dtype, device=Mt.device)
+    with torch.cuda.device(Mt.device):
+        _check(load().cagp_gram_mtm(dtype_code(Mt.dtype), _ptr(Mt), m, m, k, _ptr(B), _stream(Mt)), "cagp_gram_mtm")
+    return B
+
+
+def assemble_cotangent(Mt, row_offset, n_total, W, Abar, cbar, s_local, yt_local):
+    _require_cuda(Mt, W, Abar, cbar, s_local, yt_local)
+    k, m = Mt.shape
+    Gt = torch.empty((k, m), dtype=Mt.dtype, device=Mt.device)
+    with torch.cuda.device(Mt.device):
+        _check(load().cagp_assemble_cotangent(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(W),
+                                              _ptr(Abar), _ptr(cbar), _ptr(s_local), _ptr(yt_local), _ptr(Gt), m,
+                                              _stream(Mt)), "cagp_assemble_cotangent")
+    return Gt
+
+
+def project_rows_bwd(Mt, row_offset, n_total, Abar, cbar):
+    _require_cuda(Mt, Abar, cbar)
+    k, m = Mt.shape
+    s_dir = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
+    yt_bar = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
+    with torch.cuda.device(Mt.device):
+        _check(load().cagp_project_rows_bwd(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(Abar),
+                                            _ptr(cbar), _ptr(s_dir), _ptr(yt_bar), _stream(Mt)),
+               "cagp_project_rows_bwd")
+    return s_dir, yt_bar
+
+
+def predict_moments(Mt, w, Pinv, variance, mean_const):
+    _require_cuda(Mt, w, Pinv)
+    k, m = Mt.shape
+    lib = load()
+    scalars = torch.stack([variance.reshape(()).to(Mt.dtype), mean_const.reshape(()).to(Mt.dtype)]).contiguous()
+    ws_bytes = lib.cagp_predict_ws_bytes(dtype_code(Mt.dtype), m, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Mt.device)
+    mean = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
+    var = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
+    with torch.cuda.device(Mt.device):
+        _check(lib.cagp_predict_moments(dtype_code(Mt.dtype), _ptr(Mt), m, m, k, _ptr(w), _ptr(Pinv), _ptr(scalars),
+                                        _ptr(mean), _ptr(var), _ptr(ws), ws_bytes, _stream(Mt)),
+               "cagp_predict_moments")
+    return mean, var

@@ -1,0 +1,407 @@
+// C ABI of libcagp_b200.so: argument checking, kernel selection and launches.  See
+// include/cagp_b200.h for the contract of each entry point.
+#include "../../include/cagp_b200.h"
+
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "aux_kernels.cuh"
+#include "ks_blocksparse.cuh"
+#include "ks_dense.cuh"
+#include "ks_sym.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CAGP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return CAGP_OK;
+}
+
+// one cuBLAS handle per device, created lazily (the only global state of the library)
+std::mutex g_handle_mu;
+cublasHandle_t g_handles[64] = {nullptr};
+
+int get_handle(cudaStream_t stream, cublasHandle_t* out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(CAGP_ERR_CUDA, "cudaGetDevice failed");
+    std::lock_guard<std::mutex> lock(g_handle_mu);
+    if (!g_handles[dev]) {
+        if (cublasCreate(&g_handles[dev]) != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublasCreate failed");
+        cublasSetPointerMode(g_handles[dev], CUBLAS_POINTER_MODE_HOST);
+        cublasSetMathMode(g_handles[dev], CUBLAS_PEDANTIC_MATH);  // true fp32 for the f32 path
+    }
+    if (cublasSetStream(g_handles[dev], stream) != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublasSetStream failed");
+    *out = g_handles[dev];
+    return CAGP_OK;
+}
+
+int check_desc(const cagp_kernel_desc* kd, int d) {
+    if (!kd) return fail(CAGP_ERR_INVALID, "kernel descriptor is null");
+    if (kd->family < 0 || kd->family > 3) return fail(CAGP_ERR_INVALID, "unknown kernel family %d", kd->family);
+    if (kd->dtype != CAGP_F32 && kd->dtype != CAGP_F64) return fail(CAGP_ERR_INVALID, "unknown dtype %d", kd->dtype);
+    if (d < 1) return fail(CAGP_ERR_INVALID, "input dimension must be >= 1");
+    if (kd->n_lengthscale != 1 && kd->n_lengthscale != d)
+        return fail(CAGP_ERR_INVALID, "n_lengthscale must be 1 or d (%d), got %d", d, kd->n_lengthscale);
+    if (!kd->lengthscale) return fail(CAGP_ERR_INVALID, "lengthscale pointer is null");
+    if (cagp_padded_dim(d) < 0) return fail(CAGP_ERR_UNSUPPORTED, "input dimension %d > 32 is not supported", d);
+    return CAGP_OK;
+}
+
+template <typename F>
+int dispatch_dim(int dp, F&& f) {
+    switch (dp) {
+        case 1: return f(std::integral_constant<int, 1>{});
+        case 2: return f(std::integral_constant<int, 2>{});
+        case 3: return f(std::integral_constant<int, 3>{});
+        case 4: return f(std::integral_constant<int, 4>{});
+        case 6: return f(std::integral_constant<int, 6>{});
+        case 8: return f(std::integral_constant<int, 8>{});
+        case 12: return f(std::integral_constant<int, 12>{});
+        case 16: return f(std::integral_constant<int, 16>{});
+        case 24: return f(std::integral_constant<int, 24>{});
+        case 32: return f(std::integral_constant<int, 32>{});
+    }
+    return fail(CAGP_ERR_UNSUPPORTED, "padded dimension %d not instantiated", dp);
+}
+template <typename F>
+int dispatch_family(int fam, F&& f) {
+    switch (fam) {
+        case CAGP_RBF: return f(std::integral_constant<int, cagp::RBF>{});
+        case CAGP_MATERN12: return f(std::integral_constant<int, cagp::MATERN12>{});
+        case CAGP_MATERN32: return f(std::integral_constant<int, cagp::MATERN32>{});
+        case CAGP_MATERN52: return f(std::integral_constant<int, cagp::MATERN52>{});
+    }
+    return fail(CAGP_ERR_INVALID, "unknown family");
+}
+
+// rows per thread as a function of the (padded) dimension: keep coordinates in registers
+template <int D>
+struct RowsPerThread {
+    static constexpr int value = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
+};
+template <int D>
+struct ColsPerStage {
+    static constexpr int value = D <= 8 ? 256 : 128;
+};
+
+int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <typename T>
+int fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+             int64_t ld2, int d, const void* s, int k, void* Mt, int64_t ldm, cudaStream_t stream) {
+    const int dp = cagp_padded_dim(d);
+    return dispatch_dim(dp, [&](auto dc) {
+        return dispatch_family(kd->family, [&](auto fc) {
+            constexpr int D = decltype(dc)::value;
+            constexpr int FAM = decltype(fc)::value;
+            constexpr int R = RowsPerThread<D>::value;
+            constexpr int NT = 128;
+            constexpr int JC = ColsPerStage<D>::value;
+            cagp::FwdArgs<T> a;
+            a.xs1 = (const T*)xs1; a.ld1 = ld1; a.m = m;
+            a.xs2 = (const T*)xs2; a.ld2 = ld2;
+            a.s = (const T*)s;
+            a.lay = cagp::BlockLayout{n, k, n / k};
+            a.Mt = (T*)Mt; a.ldm = ldm;
+            const int64_t gx = (m + NT * R - 1) / (NT * R);
+            const int64_t target = (int64_t)num_sms() * 4 * 32;
+            int64_t gy = (target + gx - 1) / gx;
+            if (gy > k) gy = k;
+            if (gy < 1) gy = 1;
+            if (gy > 65535) gy = 65535;
+            a.blocks_per_cta = (int)((k + gy - 1) / gy);
+            gy = (k + a.blocks_per_cta - 1) / a.blocks_per_cta;
+            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
+            auto kern = cagp::ks_fwd_kernel<T, D, FAM, R, NT, JC>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+            return check_launch("ks_fwd_kernel");
+        });
+    });
+}
+
+template <typename T>
+struct BwdPlan {
+    int tiles_main, tiles_last, n_ichunks;
+    int64_t ichunk, gx;
+};
+
+template <typename T, int D>
+BwdPlan<T> plan_bwd(int64_t m, int64_t n, int k) {
+    constexpr int R = RowsPerThread<D>::value;
+    constexpr int NT = 128;
+    cagp::BlockLayout lay{n, k, n / k};
+    BwdPlan<T> pl;
+    pl.tiles_main = (int)((lay.bs + NT * R - 1) / (NT * R));
+    if (pl.tiles_main < 1) pl.tiles_main = 1;
+    pl.tiles_last = (int)((lay.len(k - 1) + NT * R - 1) / (NT * R));
+    if (pl.tiles_last < 1) pl.tiles_last = 1;
+    pl.gx = (int64_t)(k - 1) * pl.tiles_main + pl.tiles_last;
+    const int64_t target = (int64_t)num_sms() * 4 * 32;
+    int64_t gy = (target + pl.gx - 1) / pl.gx;
+    const int64_t max_chunks = (m + 2047) / 2048;  // at least 2048 streamed points per CTA
+    if (gy > max_chunks) gy = max_chunks;
+    if (gy > 64) gy = 64;
+    if (gy < 1) gy = 1;
+    pl.ichunk = (m + gy - 1) / gy;
+    pl.n_ichunks = (int)((m + pl.ichunk - 1) / pl.ichunk);
+    return pl;
+}
+
+template <typename T>
+size_t bwd_ws_bytes(int64_t m, int64_t n, int d, int k, int nls_pad) {
+    // upper bound independent of D: n_ichunks <= 64, gx <= k * ceil(...)
+    const int dp = cagp_padded_dim(d);
+    size_t bytes = 0;
+    dispatch_dim(dp, [&](auto dc) {
+        constexpr int D = decltype(dc)::value;
+        auto pl = plan_bwd<T, D>(m, n, k);
+        bytes = ((size_t)pl.n_ichunks * (size_t)n + (size_t)pl.n_ichunks * (size_t)pl.gx * (size_t)nls_pad) * sizeof(T);
+        return 0;
+    });
+    return bytes + 256;
+}
+
+template <typename T>
+int bwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+             int64_t ld2, int d, const void* s, int k, const void* Gt, int64_t ldg, void* s_bar, void* ls_bar,
+             void* ws, size_t ws_bytes, cudaStream_t stream) {
+    const int dp = cagp_padded_dim(d);
+    const bool ard = kd->n_lengthscale > 1;
+    return dispatch_dim(dp, [&](auto dc) {
+        return dispatch_family(kd->family, [&](auto fc) {
+            constexpr int D = decltype(dc)::value;
+            constexpr int FAM = decltype(fc)::value;
+            constexpr int R = RowsPerThread<D>::value;
+            constexpr int NT = 128;
+            constexpr int JC = ColsPerStage<D>::value;
+            auto pl = plan_bwd<T, D>(m, n, k);
+            const int nls = ard ? D : 1;
+            const size_t need = ((size_t)pl.n_ichunks * n + (size_t)pl.n_ichunks * pl.gx * nls) * sizeof(T);
+            if (ws_bytes < need) return fail(CAGP_ERR_WORKSPACE, "ks bwd workspace: need %zu bytes, got %zu", need, ws_bytes);
+            cagp::BwdArgs<T> a;
+            a.xs1 = (const T*)xs1; a.ld1 = ld1; a.m = m;
+            a.xs2 = (const T*)xs2; a.ld2 = ld2;
+            a.s = (const T*)s;
+            a.lay = cagp::BlockLayout{n, k, n / k};
+            a.Gt = (const T*)Gt; a.ldg = ldg;
+            a.sbar_part = (T*)ws;
+            a.ls_part = (T*)ws + (size_t)pl.n_ichunks * n;
+            a.tiles_main = pl.tiles_main;
+            a.ichunk = pl.ichunk;
+            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
+            dim3 grid((unsigned)pl.gx, (unsigned)pl.n_ichunks);
+            if (ard) {
+                auto kern = cagp::ks_bwd_kernel<T, D, FAM, true, R, NT, JC>;
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kern<<<grid, NT, smem, stream>>>(a);
+            } else {
+                auto kern = cagp::ks_bwd_kernel<T, D, FAM, false, R, NT, JC>;
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kern<<<grid, NT, smem, stream>>>(a);
+            }
+            int rc = check_launch("ks_bwd_kernel");
+            if (rc) return rc;
+            // deterministic reduction of the partials
+            const int64_t nparts = (int64_t)pl.n_ichunks * pl.gx;
+            cagp::bwd_finalize_kernel<T><<<dim3((unsigned)((n + 255) / 256) + 1), 256, 0, stream>>>(
+                a.sbar_part, pl.n_ichunks, n, (T*)s_bar, a.ls_part, nparts, nls, kd->n_lengthscale,
+                (const T*)kd->lengthscale, (T)cagp::family_grad_const(kd->family), (T*)ls_bar);
+            return check_launch("bwd_finalize_kernel");
+        });
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cagp_last_error_string(void) { return g_err; }
+int cagp_version(void) { return 100; }
+
+int cagp_padded_dim(int32_t d) {
+    static const int dims[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    for (int v : dims)
+        if (d <= v) return v;
+    return -1;
+}
+
+int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d, void* xs, int64_t ld,
+                      cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!X || !xs || n < 1 || ld < n) return fail(CAGP_ERR_INVALID, "scale_inputs: bad X/xs/n/ld");
+    const int dp = cagp_padded_dim(d);
+    const double c = cagp::family_scale(kd->family);
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)dp);
+    if (kd->dtype == CAGP_F64)
+        cagp::scale_inputs_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)X, n, d, (const double*)kd->lengthscale, kd->n_lengthscale, c, (double*)xs, ld);
+    else
+        cagp::scale_inputs_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, n, d, (const float*)kd->lengthscale, kd->n_lengthscale, (float)c, (float*)xs, ld);
+    return check_launch("scale_inputs_kernel");
+}
+
+int cagp_ks_blocksparse_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2,
+                            int64_t n, int64_t ld2, int32_t d, const void* s, int32_t k, void* Mt, int64_t ldm,
+                            cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs1 || !xs2 || !s || !Mt) return fail(CAGP_ERR_INVALID, "ks fwd: null pointer");
+    if (m < 1 || n < 1 || k < 1 || ld1 < m || ld2 < n || ldm < m) return fail(CAGP_ERR_INVALID, "ks fwd: bad shape");
+    if (kd->dtype == CAGP_F64) return fwd_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, s, k, Mt, ldm, (cudaStream_t)stream);
+    return fwd_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, s, k, Mt, ldm, (cudaStream_t)stream);
+}
+
+size_t cagp_ks_bwd_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d, int32_t k) {
+    if (check_desc(kd, d) || m < 1 || n < 1 || k < 1) return 0;
+    const int nls = kd->n_lengthscale > 1 ? cagp_padded_dim(d) : 1;
+    return kd->dtype == CAGP_F64 ? bwd_ws_bytes<double>(m, n, d, k, nls) : bwd_ws_bytes<float>(m, n, d, k, nls);
+}
+
+int cagp_ks_blocksparse_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2,
+                            int64_t n, int64_t ld2, int32_t d, const void* s, int32_t k, const void* Gt, int64_t ldg,
+                            void* s_bar, void* ls_bar, void* ws, size_t ws_bytes, cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs1 || !xs2 || !s || !Gt || !s_bar || !ls_bar || !ws) return fail(CAGP_ERR_INVALID, "ks bwd: null pointer");
+    if (m < 1 || n < 1 || k < 1 || ld1 < m || ld2 < n || ldg < m) return fail(CAGP_ERR_INVALID, "ks bwd: bad shape");
+    if (kd->dtype == CAGP_F64)
+        return bwd_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, s, k, Gt, ldg, s_bar, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+    return bwd_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, s, k, Gt, ldg, s_bar, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int cagp_project_rows(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total,
+                      int32_t k, const void* s, const void* yt, void* A, void* c, cagp_stream_t stream) {
+    if (!Mt || !s || !yt || !A || !c) return fail(CAGP_ERR_INVALID, "project_rows: null pointer");
+    if (m < 1 || k < 1 || ldm < m || row_offset < 0 || row_offset + m > n_total) return fail(CAGP_ERR_INVALID, "project_rows: bad shape");
+    cagp::BlockLayout lay{n_total, k, n_total / k};
+    if (dtype == CAGP_F64)
+        cagp::project_rows_kernel<double><<<k, 256, 0, (cudaStream_t)stream>>>((const double*)Mt, ldm, m, row_offset, lay, (const double*)s, (const double*)yt, (double*)A, (double*)c);
+    else if (dtype == CAGP_F32)
+        cagp::project_rows_kernel<float><<<k, 256, 0, (cudaStream_t)stream>>>((const float*)Mt, ldm, m, row_offset, lay, (const float*)s, (const float*)yt, (float*)A, (float*)c);
+    else
+        return fail(CAGP_ERR_INVALID, "unknown dtype");
+    return check_launch("project_rows_kernel");
+}
+
+int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B, cagp_stream_t stream) {
+    if (!Mt || !B || m < 1 || k < 1 || ldm < m) return fail(CAGP_ERR_INVALID, "gram_mtm: bad argument");
+    if (m > 0x7fffffffLL || ldm > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "gram_mtm: m exceeds int32 (shard rows)");
+    cublasHandle_t h;
+    if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
+    // Mt row-major (k, ldm) == column-major (ldm, k) matrix M with m valid rows: B = M^T M.
+    // Row-major "upper" of B is column-major "lower".
+    cublasStatus_t st;
+    if (dtype == CAGP_F64) {
+        const double one = 1.0, zero = 0.0;
+        st = cublasDsyrk(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, k, (int)m, &one, (const double*)Mt, (int)ldm, &zero, (double*)B, k);
+        if (st == CUBLAS_STATUS_SUCCESS) cagp::mirror_lower_kernel<double><<<dim3((k + 15) / 16, (k + 15) / 16), dim3(16, 16), 0, (cudaStream_t)stream>>>((double*)B, k);
+    } else if (dtype == CAGP_F32) {
+        const float one = 1.f, zero = 0.f;
+        st = cublasSsyrk(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, k, (int)m, &one, (const float*)Mt, (int)ldm, &zero, (float*)B, k);
+        if (st == CUBLAS_STATUS_SUCCESS) cagp::mirror_lower_kernel<float><<<dim3((k + 15) / 16, (k + 15) / 16), dim3(16, 16), 0, (cudaStream_t)stream>>>((float*)B, k);
+    } else {
+        return fail(CAGP_ERR_INVALID, "unknown dtype");
+    }
+    if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas syrk failed with status %d", (int)st);
+    return check_launch("mirror_lower_kernel");
+}
+
+int cagp_assemble_cotangent(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total,
+                            int32_t k, const void* W, const void* Abar, const void* cbar, const void* s, const void* yt,
+                            void* Gt, int64_t ldg, cagp_stream_t stream) {
+    if (!Mt || !W || !Abar || !cbar || !s || !yt || !Gt) return fail(CAGP_ERR_INVALID, "assemble_cotangent: null pointer");
+    if (m < 1 || k < 1 || ldm < m || ldg < m || row_offset < 0 || row_offset + m > n_total) return fail(CAGP_ERR_INVALID, "assemble_cotangent: bad shape");
+    if (m > 0x7fffffffLL || ldm > 0x7fffffffLL || ldg > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "assemble_cotangent: m exceeds int32");
+    cublasHandle_t h;
+    if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
+    cagp::BlockLayout lay{n_total, k, n_total / k};
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)k);
+    cublasStatus_t st;
+    // column-major: G (m x k, ld ldg) = M (m x k, ld ldm) * W^T (k x k)  + prefilled outer terms
+    if (dtype == CAGP_F64) {
+        cagp::cotangent_prefill_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(m, row_offset, lay, (const double*)Abar, (const double*)cbar, (const double*)s, (const double*)yt, (double*)Gt, ldg);
+        const double one = 1.0;
+        st = cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const double*)Mt, (int)ldm, (const double*)W, k, &one, (double*)Gt, (int)ldg);
+    } else if (dtype == CAGP_F32) {
+        cagp::cotangent_prefill_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(m, row_offset, lay, (const float*)Abar, (const float*)cbar, (const float*)s, (const float*)yt, (float*)Gt, ldg);
+        const float one = 1.f;
+        st = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const float*)Mt, (int)ldm, (const float*)W, k, &one, (float*)Gt, (int)ldg);
+    } else {
+        return fail(CAGP_ERR_INVALID, "unknown dtype");
+    }
+    if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas gemm failed with status %d", (int)st);
+    return check_launch("cotangent_prefill_kernel");
+}
+
+int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total,
+                          int32_t k, const void* Abar, const void* cbar, void* s_dir, void* yt_bar, cagp_stream_t stream) {
+    if (!Mt || !Abar || !cbar || !s_dir || !yt_bar) return fail(CAGP_ERR_INVALID, "project_rows_bwd: null pointer");
+    if (m < 1 || k < 1 || ldm < m || row_offset < 0 || row_offset + m > n_total) return fail(CAGP_ERR_INVALID, "project_rows_bwd: bad shape");
+    cagp::BlockLayout lay{n_total, k, n_total / k};
+    const unsigned grid = (unsigned)((m + 255) / 256);
+    if (dtype == CAGP_F64)
+        cagp::project_rows_bwd_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)Mt, ldm, m, row_offset, lay, (const double*)Abar, (const double*)cbar, (double*)s_dir, (double*)yt_bar);
+    else if (dtype == CAGP_F32)
+        cagp::project_rows_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)Mt, ldm, m, row_offset, lay, (const float*)Abar, (const float*)cbar, (float*)s_dir, (float*)yt_bar);
+    else
+        return fail(CAGP_ERR_INVALID, "unknown dtype");
+    return check_launch("project_rows_bwd_kernel");
+}
+
+size_t cagp_predict_ws_bytes(int32_t dtype, int64_t m, int32_t k) {
+    const size_t es = dtype == CAGP_F64 ? 8 : 4;
+    return (size_t)k * (size_t)m * es;
+}
+
+int cagp_predict_moments(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, const void* w,
+                         const void* Pinv, const void* scalars, void* mean, void* var, void* ws, size_t ws_bytes,
+                         cagp_stream_t stream) {
+    if (!Mt || !w || !Pinv || !scalars || !mean || !var || !ws) return fail(CAGP_ERR_INVALID, "predict_moments: null pointer");
+    if (m < 1 || k < 1 || ldm < m) return fail(CAGP_ERR_INVALID, "predict_moments: bad shape");
+    if (m > 0x7fffffffLL || ldm > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "predict_moments: m exceeds int32");
+    if (ws_bytes < cagp_predict_ws_bytes(dtype, m, k)) return fail(CAGP_ERR_WORKSPACE, "predict_moments: workspace too small");
+    cublasHandle_t h;
+    if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
+    cublasStatus_t st;
+    const unsigned grid = (unsigned)((m + 255) / 256);
+    // column-major: Z (m x k, ld m) = M (m x k) * Pinv (k x k, symmetric)
+    if (dtype == CAGP_F64) {
+        const double one = 1.0, zero = 0.0;
+        st = cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const double*)Mt, (int)ldm, (const double*)Pinv, k, &zero, (double*)ws, (int)m);
+        if (st == CUBLAS_STATUS_SUCCESS)
+            cagp::predict_moments_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)Mt, ldm, (const double*)ws, m, m, k, (const double*)w, (const double*)scalars, (double*)mean, (double*)var);
+    } else if (dtype == CAGP_F32) {
+        const float one = 1.f, zero = 0.f;
+        st = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const float*)Mt, (int)ldm, (const float*)Pinv, k, &zero, (float*)ws, (int)m);
+        if (st == CUBLAS_STATUS_SUCCESS)
+            cagp::predict_moments_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)Mt, ldm, (const float*)ws, m, m, k, (const float*)w, (const float*)scalars, (float*)mean, (float*)var);
+    } else {
+        return fail(CAGP_ERR_INVALID, "unknown dtype");
+    }
+    if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas gemm failed with status %d", (int)st);
+    return check_launch("predict_moments_kernel");
+}
+
+}  // extern "C"

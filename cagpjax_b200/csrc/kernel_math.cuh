@@ -1,0 +1,161 @@
+// Per-pair kernel arithmetic for the CaGP hot path (sm_100a).
+//
+// The kernels work on PRE-SCALED coordinates (cagp_scale_inputs): with q = sum_t (a_t - b_t)^2,
+//   RBF       K' = 2^(-q)                         scale c = sqrt(0.5 log2 e) / l
+//   Matern12  K' = 2^(-sqrt q)                    scale c = log2 e / l
+//   Matern32  K' = (1 + ln2 sqrt q) 2^(-sqrt q)   scale c = sqrt 3 log2 e / l
+//   Matern52  K' = (1 + r + r^2/3) 2^(-sqrt q), r = ln2 sqrt q,  scale c = sqrt 5 log2 e / l
+// which restates the GPJax formulas the reference evaluates through
+// DenseKernelComputation.cross_covariance (operators/lazy_kernel.py:83-85) with unit variance.
+//
+// d K'/d lengthscale_t = H * q_t * (family constant / lengthscale_t), q_t = (a_t - b_t)^2, where
+//   RBF H = K' (const 2 ln2), Matern12 H = K'/sqrt q (const ln2), Matern32 H = 2^(-sqrt q)
+//   (const ln2^2), Matern52 H = (1 + r) 2^(-sqrt q) / 3 (const ln2^2).
+//
+// fp64 2^(-u): the fp64 pipe is the roofline of this path (no SFU for doubles), so instead of
+// libm exp (17 fp64 issue slots) we use a 2048-entry table of 2^(-j/2048) staged in shared
+// memory, magic-number range reduction (3 DADD) and a cubic (3 DFMA + 1 DMUL): 7 fp64 slots,
+// max error ~1 ulp.  fp32 uses MUFU.EX2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cagp {
+
+enum Family : int { RBF = 0, MATERN12 = 1, MATERN32 = 2, MATERN52 = 3 };
+
+constexpr int kExpTabBits = 11;
+constexpr int kExpTabSize = 1 << kExpTabBits;
+
+__device__ const double g_exp2_tab[kExpTabSize] = {
+#include "exp2_table.inc"
+};
+
+template <typename T>
+struct ExpTab;
+
+template <>
+struct ExpTab<double> {
+    static constexpr int kSmemElems = kExpTabSize;
+    __device__ static unsigned load(double* tab, int tid, int nthreads) {
+        for (int i = tid; i < kExpTabSize; i += nthreads) tab[i] = g_exp2_tab[i];
+        return (unsigned)__cvta_generic_to_shared(tab);
+    }
+};
+template <>
+struct ExpTab<float> {
+    static constexpr int kSmemElems = 0;
+    __device__ static unsigned load(float*, int, int) { return 0u; }
+};
+
+// 2^(-u) for u >= 0 (u may be huge or +inf: the result is then ~2^-1000 ~ 0).
+// `tab_s` is the shared-window address of the 2048-entry table of 2^(-(j + 1/2)/2048)... see below.
+//
+// magic = 1.5 * 2^38 has ulp 2^-14, so the low mantissa word of t = u + magic is round(u * 2^14)
+// (u < 2^18).  Bits 3..13 of that word index the table (byte offset = lo & 0x3ff8, one LOP3);
+// bits 14.. are the integer part that goes into the exponent.  Clearing bits 0..2 of t and
+// subtracting (magic - 2^-12) gives the centre of the table cell, so f = u - centre lies in
+// [-2^-12, 2^-12] and 2^(-f) is a cubic (Taylor remainder 3.4e-17).
+__device__ __forceinline__ double exp2neg(double u, unsigned tab_s) {
+    constexpr double kMagic = 412316860416.0;              // 1.5 * 2^38
+    constexpr double kMagicC = 412316860416.0 - 0x1p-12;   // cell centre offset
+    constexpr int kMagicHi = 0x42580000;                   // high word of kMagic
+    const double t = u + kMagic;
+    unsigned lo = (unsigned)__double2loint(t);
+    const int hi = __double2hiint(t);
+    const double tc = __hiloint2double(hi, (int)(lo & ~7u));
+    const double f = u - (tc - kMagicC);
+    double tv;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(tab_s + (lo & 0x3ff8u)));
+    constexpr double c1 = -0.693147180559945309417232121458;
+    constexpr double c2 = 0.240226506959100712333551263163;
+    constexpr double c3 = -0.0555041086648215799531422637686;
+    const double p = fma(f, fma(f, fma(f, c3, c2), c1), 1.0);
+    // clamp the integer part at 1000 (also when u >= 2^18 spilled into the high word)
+    lo = (hi == kMagicHi) ? lo : 0xffffffffu;
+    lo = min(lo, 1000u << 14);
+    const int thi = __double2hiint(tv) - (int)((lo & ~0x3fffu) << 6);
+    return __hiloint2double(thi, __double2loint(tv)) * p;
+}
+
+__device__ __forceinline__ float exp2neg(float u, unsigned) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-u));
+    return r;
+}
+
+__device__ __forceinline__ double fast_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float fast_sqrt(float x) { return sqrtf(x); }
+
+template <typename T>
+struct Consts;
+template <>
+struct Consts<double> {
+    static constexpr double ln2 = 0.693147180559945309417232121458;
+    static constexpr double tiny = 1e-300;  // scaled analogue of GPJax's max(sq, 1e-36) guard
+};
+template <>
+struct Consts<float> {
+    static constexpr float ln2 = 0.693147180559945309417232121458f;
+    static constexpr float tiny = 1e-36f;
+};
+
+// K' from q.
+template <typename T, int FAM>
+__device__ __forceinline__ T kernel_value(T q, unsigned tab) {
+    if (FAM == RBF) {
+        return exp2neg(q, tab);
+    } else {
+        const T tp = fast_sqrt(q);
+        const T e = exp2neg(tp, tab);
+        if (FAM == MATERN12) return e;
+        const T r = tp * Consts<T>::ln2;
+        if (FAM == MATERN32) return fma(r, e, e);
+        // MATERN52: (1 + r + r^2/3) e
+        return fma(fma(r, T(1.0 / 3.0), T(1)), r, T(1)) * e;
+    }
+}
+
+// K' and H (see header comment) from q.
+template <typename T, int FAM>
+__device__ __forceinline__ void kernel_value_grad(T q, unsigned tab, T& kv, T& h) {
+    if (FAM == RBF) {
+        kv = exp2neg(q, tab);
+        h = kv;
+    } else {
+        const T tp = fast_sqrt(q);
+        const T e = exp2neg(tp, tab);
+        const T r = tp * Consts<T>::ln2;
+        if (FAM == MATERN12) {
+            kv = e;
+            h = (q > Consts<T>::tiny) ? e / tp : T(0);
+        } else if (FAM == MATERN32) {
+            kv = fma(r, e, e);
+            h = e;
+        } else {
+            kv = fma(fma(r, T(1.0 / 3.0), T(1)), r, T(1)) * e;
+            h = fma(r, e, e) * T(1.0 / 3.0);
+        }
+    }
+}
+
+// host+device: coordinate scale and gradient constant per family
+__host__ __device__ inline double family_scale(int fam) {
+    const double log2e = 1.44269504088896340735992468100189214;
+    switch (fam) {
+        case RBF: return 0.84932180028801904272150283410288961;  // sqrt(0.5 * log2 e)
+        case MATERN12: return log2e;
+        case MATERN32: return 1.73205080756887729352744634150587237 * log2e;
+        default: return 2.23606797749978969640917366873127624 * log2e;
+    }
+}
+__host__ __device__ inline double family_grad_const(int fam) {
+    const double ln2 = 0.693147180559945309417232121458;
+    switch (fam) {
+        case RBF: return 2.0 * ln2;
+        case MATERN12: return ln2;
+        default: return ln2 * ln2;
+    }
+}
+
+}  // namespace cagp

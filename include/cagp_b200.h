@@ -1,0 +1,136 @@
+/*
+ * cagp_b200.h - C ABI of the B200-native CaGP hot path (libcagp_b200.so).
+ *
+ * Every entry point is stream-ordered and non-blocking: no device allocation, no host
+ * synchronisation, no host read of device scalars.  The caller (XLA, torch, ...) owns every
+ * buffer, including scratch.  Kernel hyper-parameters are passed as DEVICE pointers because
+ * they are traced values under jit in the reference (operators/lazy_kernel.py:37-57 stores the
+ * GPJax kernel object; its lengthscale / variance are JAX arrays).
+ *
+ * Return value: 0 on success, otherwise a cagp_status code; cagp_last_error_string() gives a
+ * thread-local description.  Nothing throws across this boundary.
+ *
+ * Reference citations are relative to /root/reference/src/cagpjax.
+ *
+ * Data layout conventions
+ *   X       row-major (n, d) inputs exactly as the reference holds them (cagp.py:91).
+ *   xs      "scaled SoA" copy, shape (d, ld): xs[t*ld + i] = X[i*d + t] * c_family / lengthscale_t.
+ *           c_family folds the kernel's exponent constant and log2(e) so that the kernels
+ *           evaluate 2^(-q) (RBF) or 2^(-sqrt q) (Matern) on q = sum_t (xs1_t - xs2_t)^2.
+ *   Mt      the projected kernel matrix M' = K'(X1, X2) S stored k-major: Mt[b*ld + i] = M'[i, b]
+ *           (K' is the unit-variance kernel; the caller multiplies by `variance`).
+ *   blocks  BlockDiagonalSparse layout (operators/block_diagonal_sparse.py:49-52): block_size =
+ *           n / k, the last block absorbs n % k.
+ */
+#ifndef CAGP_B200_H_
+#define CAGP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cagp_stream_t; /* cudaStream_t */
+
+enum cagp_status {
+  CAGP_OK = 0,
+  CAGP_ERR_INVALID = 1,   /* bad argument (shape, enum, null pointer) */
+  CAGP_ERR_UNSUPPORTED = 2,
+  CAGP_ERR_CUDA = 3,      /* a CUDA runtime call / launch failed */
+  CAGP_ERR_CUBLAS = 4,
+  CAGP_ERR_WORKSPACE = 5  /* workspace too small */
+};
+
+enum cagp_family { CAGP_RBF = 0, CAGP_MATERN12 = 1, CAGP_MATERN32 = 2, CAGP_MATERN52 = 3 };
+enum cagp_dtype { CAGP_F32 = 0, CAGP_F64 = 1 };
+
+/* Stationary kernel descriptor; replaces the GPJax kernel object held by LazyKernel
+ * (operators/lazy_kernel.py:37-57).  `variance` is not used by the kernels (unit variance). */
+typedef struct cagp_kernel_desc {
+  int32_t family;            /* cagp_family */
+  int32_t dtype;             /* cagp_dtype of every floating-point buffer in the call */
+  int32_t n_lengthscale;     /* 1 (isotropic) or d (ARD) */
+  int32_t reserved;
+  const void* lengthscale;   /* device pointer, n_lengthscale elements */
+} cagp_kernel_desc;
+
+const char* cagp_last_error_string(void);
+int cagp_version(void);
+
+/* Coordinate dimension the kernels are instantiated for: d is zero-padded up to this value
+ * (1, 2, 3, 4, 6, 8, 12, 16, 24, 32); returns -1 if d > 32.  xs buffers have this many rows. */
+int cagp_padded_dim(int32_t d);
+
+/* xs = scale_and_transpose(X).  Replaces `x / lengthscale` inside the GPJax kernel call made at
+ * operators/lazy_kernel.py:83-85.  X (n, d) row-major; xs (cagp_padded_dim(d), ld), ld >= n; padding rows are zeroed. */
+int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d, void* xs,
+                      int64_t ld, cagp_stream_t stream);
+
+/* Mt = (K'(X1, X2) S)^T for a BlockDiagonalSparse S with non-zeros `s` (n) and k blocks.
+ * Replaces LazyKernel._matmat applied to to_dense(BlockDiagonalSparse)
+ * (operators/lazy_kernel.py:79-90 x operators/block_diagonal_sparse.py:48-70) without
+ * materialising K or the dense S.  xs1 (d, ld1) has m points, xs2 (d, ld2) has n points.
+ * Mt (k, ldm), ldm >= m. */
+int cagp_ks_blocksparse_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1,
+                            const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* s,
+                            int32_t k, void* Mt, int64_t ldm, cagp_stream_t stream);
+
+/* Reverse mode of cagp_ks_blocksparse_fwd with respect to the lengthscale(s) and s, given
+ * Gt[b*ldg + i] = dL/dM'[i, b] (k, ldg):
+ *   s_bar[j]   = sum_i K'(x1_i, x2_j) Gt[blk(j)][i]
+ *   ls_bar[t]  = sum_ij Gt[blk(j)][i] s_j dK'(x1_i, x2_j)/d lengthscale_t
+ * This is what JAX reverse mode produces through lax.map + checkpoint in the reference
+ * (operators/lazy_kernel.py:88-89; the reference has no custom VJP).  K' is recomputed, never
+ * stored.  `ws` is scratch of cagp_ks_bwd_ws_bytes() bytes.  s_bar (n), ls_bar (n_lengthscale)
+ * are overwritten. */
+size_t cagp_ks_bwd_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d, int32_t k);
+int cagp_ks_blocksparse_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1,
+                            const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* s,
+                            int32_t k, const void* Gt, int64_t ldg, void* s_bar, void* ls_bar,
+                            void* ws, size_t ws_bytes, cagp_stream_t stream);
+
+/* A'[a][b] = sum_{i in block a} s_i M'[i, b]  (k, k) row-major and c'[b] = sum_i M'[i, b] yt_i,
+ * for the m rows held by the caller: global row index of local row i is row_offset + i (row
+ * sharding); n_total is the global n that defines the block layout.  Replaces
+ * BlockDiagonalSparse._rmatmat (operators/block_diagonal_sparse.py:72-95) applied to K S and the
+ * contraction (K S)^T (y - mean) used by predict (models/cagp.py:160-163). */
+int cagp_project_rows(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,
+                      int64_t n_total, int32_t k, const void* s, const void* yt, void* A, void* c,
+                      cagp_stream_t stream);
+
+/* B' = M'^T M' (k, k), full symmetric matrix, via cuBLAS syrk + mirror.  Replaces the lazy
+ * inv_congruence_transform / cola.diag chain (solvers/cholesky.py:57-63, distributions.py:53-56)
+ * whose trace only needs this k x k Gram matrix. */
+int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B,
+                  cagp_stream_t stream);
+
+/* Gt = W Mt + outer terms:  Gt[b][i] = sum_c W[b][c] Mt[c][i] + Abar[blk(i)][b] s_i + cbar[b] yt_i.
+ * W (k, k) row-major (the caller passes Bbar + Bbar^T).  Cotangent of M' through A', B', c'. */
+int cagp_assemble_cotangent(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,
+                            int64_t n_total, int32_t k, const void* W, const void* Abar,
+                            const void* cbar, const void* s, const void* yt, void* Gt, int64_t ldg,
+                            cagp_stream_t stream);
+
+/* Direct (non-kernel) cotangents of the projections for the caller's m rows:
+ *   s_dir[i] = sum_b Abar[blk(i)][b] M'[i, b],   yt_bar[i] = sum_b cbar[b] M'[i, b]. */
+int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,
+                          int64_t n_total, int32_t k, const void* Abar, const void* cbar, void* s_dir,
+                          void* yt_bar, cagp_stream_t stream);
+
+/* Predictive moments at the m points behind Mt = (K'(X*, X) S)^T (models/cagp.py:160-167,
+ * distributions.py:48-56):
+ *   mean[i] = mean_const + variance * sum_b M'[i, b] w[b]
+ *   var[i]  = variance * kdiag - variance^2 * sum_{b,c} M'[i, b] Pinv[b][c] M'[i, c]
+ * Pinv (k, k) row-major symmetric; `scalars` is a device array {variance, mean_const}.
+ * `ws` holds an (k, ldm) scratch panel: cagp_predict_ws_bytes(). */
+size_t cagp_predict_ws_bytes(int32_t dtype, int64_t m, int32_t k);
+int cagp_predict_moments(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k,
+                         const void* w, const void* Pinv, const void* scalars, void* mean, void* var,
+                         void* ws, size_t ws_bytes, cagp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAGP_B200_H_ */
