@@ -1,0 +1,201 @@
+"""Differentiable torch entry points over the C ABI (custom VJPs of the kernel projection).
+
+The reference differentiates this path with plain JAX reverse mode through ``lax.map`` +
+``jax.checkpoint`` (operators/lazy_kernel.py:79-103); here the forward and the reverse pass are
+hand-written sm_100a kernels and these ``torch.autograd.Function``s are the custom VJP glue
+(a JAX host would wrap the same C entry points in ``jax.custom_vjp``).
+
+Row sharding: every rank holds all of X / s / y (<= 40 MB at n = 1M) and owns the
+rows ``[row_begin, row_end)`` of X1, hence of M' and of its cotangent.  The k x k partials are
+summed with one all-reduce in the forward and the n-sized cotangents with one in the backward.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+
+# --------------------------------------------------------------------------------------------
+# Row partition / process-group plumbing
+# --------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class RowShard:
+    """Rows [begin, end) of the n training points owned by this rank; ``group`` None => single GPU."""
+
+    begin: int
+    end: int
+    n: int
+    group: object = None  # torch.distributed process group (or None)
+
+    @property
+    def sharded(self) -> bool:
+        return self.group is not None
+
+    @staticmethod
+    def full(n: int) -> "RowShard":
+        return RowShard(0, n, n, None)
+
+    @staticmethod
+    def for_rank(n: int, rank: int, world: int, group=None) -> "RowShard":
+        """Even split of rows; the remainder goes to the first ranks (any split is exact, F6)."""
+        base, rem = divmod(n, world)
+        begin = rank * base + min(rank, rem)
+        end = begin + base + (1 if rank < rem else 0)
+        return RowShard(begin, end, n, group)
+
+
+def _all_reduce_sum(t: torch.Tensor, group) -> torch.Tensor:
+    if group is None:
+        return t
+    import torch.distributed as dist
+
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# Local compute (the part that runs native kernels).  Tests for the sharding logic replace this
+# with an oracle-backed callable on CPU (gloo); the product always uses the native one.
+# --------------------------------------------------------------------------------------------
+def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
+    """Returns (A', B', c', Mt, xs): partial statistics over the local rows."""
+    d = X.shape[1]
+    xs = N.scale_inputs(family, X, lengthscale)
+    xs1 = xs if not shard.sharded and shard.begin == 0 and shard.end == shard.n else xs[:, shard.begin:shard.end].contiguous()
+    Mt = N.ks_blocksparse_fwd(family, xs1, xs, d, s, k, lengthscale)
+    sl = s[shard.begin:shard.end].contiguous()
+    yl = yt[shard.begin:shard.end].contiguous()
+    A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)
+    B = N.gram_mtm(Mt)
+    return A, B, c, Mt, xs, xs1
+
+
+def native_local_backward(family, X, lengthscale, s, yt, k, shard: RowShard, saved, Abar, Bbar, cbar):
+    """Returns (s_bar_full_partial (n), yt_bar_local (m), ls_bar partial)."""
+    Mt, xs, xs1 = saved
+    d = X.shape[1]
+    sl = s[shard.begin:shard.end].contiguous()
+    yl = yt[shard.begin:shard.end].contiguous()
+    W = (Bbar + Bbar.T).contiguous()
+    Gt = N.assemble_cotangent(Mt, shard.begin, shard.n, W, Abar.contiguous(), cbar.contiguous(), sl, yl)
+    s_bar, ls_bar = N.ks_blocksparse_bwd(family, xs1, xs, d, s, k, Gt, lengthscale)
+    del Gt
+    s_dir, yt_bar = N.project_rows_bwd(Mt, shard.begin, shard.n, Abar.contiguous(), cbar.contiguous())
+    s_bar[shard.begin:shard.end] += s_dir
+    return s_bar, yt_bar, ls_bar
+
+
+class ProjectStats(torch.autograd.Function):
+    """(X, lengthscale, s, yt) -> (A', B', c') with A' = S^T K' S, B' = (K'S)^T (K'S), c' = (K'S)^T yt.
+
+    K' is the unit-variance kernel.  Non-differentiable w.r.t. X (training inputs are data in
+    the reference path).  ``holder`` (a dict) receives the saved ``Mt`` so that predict-at-train
+    can reuse it without a second n^2 pass.
+    """
+
+    @staticmethod
+    def forward(ctx, X, lengthscale, s, yt, family, k, shard, holder, local_fwd, local_bwd):
+        local_fwd = local_fwd or native_local_forward
+        A, B, c, *saved = local_fwd(family, X, lengthscale, s, yt, k, shard)
+        if shard.sharded:
+            packed = torch.cat([A.reshape(-1), B.reshape(-1), c.reshape(-1)])
+            _all_reduce_sum(packed, shard.group)
+            kk = k * k
+            A, B, c = packed[:kk].view(k, k), packed[kk:2 * kk].view(k, k), packed[2 * kk:]
+        ctx.family, ctx.k, ctx.shard = family, k, shard
+        ctx.local_bwd = local_bwd or native_local_backward
+        ctx.saved_extra = saved
+        ctx.save_for_backward(X, lengthscale, s, yt)
+        if holder is not None:
+            holder["Mt"] = saved[0]
+            holder["shard"] = shard
+        return A, B, c
+
+    @staticmethod
+    def backward(ctx, Abar, Bbar, cbar):
+        X, lengthscale, s, yt = ctx.saved_tensors
+        shard = ctx.shard
+        s_bar, yt_bar_local, ls_bar = ctx.local_bwd(ctx.family, X, lengthscale, s, yt, ctx.k, shard,
+                                                    ctx.saved_extra, Abar, Bbar, cbar)
+        if shard.sharded or yt_bar_local.shape[0] != shard.n:
+            yt_bar = torch.zeros_like(yt)
+            yt_bar[shard.begin:shard.end] = yt_bar_local
+        else:
+            yt_bar = yt_bar_local
+        if shard.sharded:
+            n = shard.n
+            packed = torch.cat([s_bar, yt_bar, ls_bar.reshape(-1)])
+            _all_reduce_sum(packed, shard.group)
+            s_bar, yt_bar, ls_bar = packed[:n], packed[n:2 * n], packed[2 * n:]
+        return None, ls_bar.reshape(lengthscale.shape), s_bar, yt_bar, None, None, None, None, None, None
+
+
+def project_stats(family: str, X, lengthscale, s, yt, k: int, shard: Optional[RowShard] = None, holder=None,
+                  local_fwd: Optional[Callable] = None, local_bwd: Optional[Callable] = None):
+    shard = shard or RowShard.full(X.shape[0])
+    return ProjectStats.apply(X, lengthscale, s, yt, family, k, shard, holder, local_fwd, local_bwd)
+
+
+class KSMatrix(torch.autograd.Function):
+    """Mt (k, m) = (K'(X1, X2) S)^T, differentiable w.r.t. lengthscale and s (not X1, X2)."""
+
+    @staticmethod
+    def forward(ctx, X1, X2, lengthscale, s, family, k):
+        d = X2.shape[1]
+        xs2 = N.scale_inputs(family, X2, lengthscale)
+        same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
+        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale)
+        Mt = N.ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale)
+        ctx.family, ctx.k, ctx.d = family, k, d
+        ctx.save_for_backward(xs1, xs2, s, lengthscale)
+        return Mt
+
+    @staticmethod
+    def backward(ctx, Gt):
+        xs1, xs2, s, lengthscale = ctx.saved_tensors
+        s_bar, ls_bar = N.ks_blocksparse_bwd(ctx.family, xs1, xs2, ctx.d, s, ctx.k, Gt.contiguous(), lengthscale)
+        return None, None, ls_bar.reshape(lengthscale.shape), s_bar, None, None
+
+
+def ks_matrix(family: str, X1, X2, lengthscale, s, k: int) -> torch.Tensor:
+    return KSMatrix.apply(X1, X2, lengthscale, s, family, k)
+
+
+# --------------------------------------------------------------------------------------------
+# Segment sums over the action blocks (n-sized, autograd-friendly torch ops)
+# --------------------------------------------------------------------------------------------
+def block_layout(n: int, n_blocks: int) -> Tuple[int, int, int]:
+    """(block_size, n_blocks_main, n_main) - operators/block_diagonal_sparse.py:49-52."""
+    block_size = n // n_blocks
+    n_blocks_main = n_blocks if n % n_blocks == 0 else n_blocks - 1
+    return block_size, n_blocks_main, n_blocks_main * block_size
+
+
+def segment_sum(v: torch.Tensor, n_blocks: int) -> torch.Tensor:
+    """Sum of ``v`` (n,) over each action block -> (n_blocks,)  (linalg/congruence.py:34-41)."""
+    n = v.shape[0]
+    block_size, n_blocks_main, n_main = block_layout(n, n_blocks)
+    if n_blocks_main > 0:
+        out = v[:n_main].reshape(n_blocks_main, block_size).sum(dim=1)
+    else:
+        out = v.new_zeros((0,))
+    if n > n_main:
+        out = torch.cat([out, v[n_main:].sum(dim=0, keepdim=True)])
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Dense right-hand side: Y = K'(X1, X2) V   (LazyKernel._matmat, operators/lazy_kernel.py:79-90)
+# --------------------------------------------------------------------------------------------
+def kernel_matmat(family: str, X1, X2, lengthscale, V: torch.Tensor) -> torch.Tensor:
+    """K'(X1, X2) @ V for dense V (n, p), differentiable w.r.t. lengthscale and V.
+
+    Every column of V is a one-block ``BlockDiagonalSparse`` (k = 1), so the block-sparse kernels
+    compute it exactly; p columns cost p kernel passes."""
+    cols = [ks_matrix(family, X1, X2, lengthscale, V[:, c].contiguous(), 1)[0] for c in range(V.shape[1])]
+    return torch.stack(cols, dim=1)

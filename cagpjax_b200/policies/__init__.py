@@ -1,0 +1,6 @@
+"""Linear solver policies (reference: policies/__init__.py)."""
+
+from .base import AbstractBatchLinearSolverPolicy, AbstractLinearSolverPolicy
+from .block_sparse import BlockSparsePolicy
+
+__all__ = ["AbstractLinearSolverPolicy", "AbstractBatchLinearSolverPolicy", "BlockSparsePolicy"]

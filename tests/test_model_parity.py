@@ -1,0 +1,114 @@
+"""ComputationAwareGP.init / predict / prior_kl / elbo and its gradients: CUDA path vs CPU oracle."""
+
+import pytest
+import torch
+
+from cagpjax_b200 import gpx
+from oracle import cagp_oracle as O
+from tests.util import make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# north-star tolerances: 1e-10 relative in float64, 1e-4 in float32
+TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+SHAPES = [(9, 1, 4), (5, 2, 2), (6, 3, 3), (1037, 3, 10), (700, 8, 64), (1000, 1, 10)]
+
+
+def neg_elbo(model, data):
+    return -model.elbo(model.init(data))
+
+
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+@pytest.mark.parametrize("n,d,k", SHAPES)
+def test_init_predict_elbo_match_oracle_f64(family, n, d, k):
+    model, data, p, x, y = make_problem(family, n, d, k, ard=(d == 3))
+    with torch.no_grad():
+        st = model.init(data)
+        ost = O.cagp_init(family, x, y, p, k)
+        tol = TOL[torch.float64]
+        # S^T K^ S (before jitter) and its factor
+        P = st.cov_prior_proj_state.A @ st.cov_prior_proj_state.A.T
+        oP = ost.L @ ost.L.T
+        assert rel_err(P, oP) < tol
+        assert rel_err(st.obs_cov_proj.diag, ost.obs_cov_proj) < tol
+        assert rel_err(st.residual_proj, ost.residual_proj) < tol
+        cond = float(torch.linalg.cond(oP))
+        assert rel_err(st.repr_weights_proj, ost.repr_weights_proj) < tol * max(1.0, cond)
+        # predictions at the training inputs and at new inputs
+        om, ov = O.cagp_predict(family, ost, p)
+        q = model.predict(st)
+        assert rel_err(q.mean, om) < tol * 10
+        assert rel_err(q.variance, ov) < tol * 10
+        g = torch.Generator().manual_seed(9)
+        z = torch.rand(33, d, generator=g, dtype=torch.float64) * 4
+        om, ov, ocov = O.cagp_predict(family, ost, p, z, full_cov=True)
+        q = model.predict(st, z.to("cuda:0"))
+        assert q.mean.shape == (33,) and q.scale.shape == (33, 33)
+        assert rel_err(q.mean, om) < tol * 10
+        assert rel_err(q.variance, ov) < tol * 10
+        assert rel_err(q.scale.to_dense(), ocov) < tol * 10
+        # KL and ELBO
+        assert rel_err(model.prior_kl(st), O.cagp_prior_kl(ost)) < tol * 10
+        oe = O.cagp_elbo(family, ost, p)
+        assert rel_err(model.elbo(st), oe) < tol
+        # the fused ELBO equals the reference's definition sum(var_exp) - KL (tests/test_models.py:284-308)
+        explicit = model.variational_expectation(st).sum() - model.prior_kl(st)
+        assert rel_err(model.elbo(st), explicit) < tol
+
+
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+@pytest.mark.parametrize("n,d,k,ard", [(9, 1, 4, False), (6, 3, 3, True), (1037, 3, 10, False), (700, 8, 64, True),
+                                       (523, 3, 7, True)])
+def test_elbo_gradients_match_oracle_f64(family, n, d, k, ard):
+    model, data, p, x, y = make_problem(family, n, d, k, ard=ard, normalize=False)
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    oval, ograds = O.elbo_and_grad_literal(family, x, y, p, k)
+    tol = TOL[torch.float64]
+    assert rel_err(-val, oval) < tol
+    names = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev",
+             "constant": "mean_constant", "nz_values": "actions"}
+    seen = 0
+    for name, g in grads.items():
+        key = names[name.split(".")[1]]
+        assert rel_err(-g.reshape(-1), ograds[key].reshape(-1)) < tol * 50, name
+        seen += 1
+    assert seen == 5
+
+
+@pytest.mark.parametrize("family", ["rbf", "matern32"])
+@pytest.mark.parametrize("n,d,k", [(9, 1, 4), (1037, 3, 10), (700, 8, 64)])
+def test_elbo_and_gradients_f32(family, n, d, k):
+    model, data, p, x, y = make_problem(family, n, d, k, dtype=torch.float32, normalize=True, obs_stddev=0.5)
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    assert val.dtype == torch.float32
+    oval, ograds = O.elbo_and_grad_literal(family, x, y, p, k)
+    assert rel_err(-val, oval) < TOL[torch.float32] * 10
+    names = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev",
+             "constant": "mean_constant", "nz_values": "actions"}
+    for name, g in grads.items():
+        key = names[name.split(".")[1]]
+        assert rel_err(-g.reshape(-1), ograds[key].reshape(-1)) < 5e-2, name
+
+
+def test_predict_no_inputs_equals_predict_train_inputs():
+    """tests/test_models.py:193-204 of the reference."""
+    model, data, p, x, y = make_problem("rbf", 300, 2, 6)
+    with torch.no_grad():
+        st = model.init(data)
+        a, b = model.predict(st), model.predict(st, data.X)
+        assert torch.allclose(a.mean, b.mean)
+        assert torch.allclose(a.variance, b.variance, atol=1e-10)
+        assert torch.allclose(a.scale.to_dense(), b.scale.to_dense(), atol=1e-7)
+
+
+def test_exact_gp_when_actions_span_everything():
+    """n_actions = n recovers the exact GP (tests/test_models.py:206-235; with BlockSparse, k = n
+    makes S an invertible diagonal matrix)."""
+    model, data, p, x, y = make_problem("rbf", 40, 1, 40, normalize=True)
+    g = torch.Generator().manual_seed(2)
+    z = torch.rand(15, 1, generator=g, dtype=torch.float64) * 4
+    with torch.no_grad():
+        q = model.predict(model.init(data), z.to("cuda:0"))
+    m, cov = O.exact_gp_predict("rbf", x, y, z, p.lengthscale, p.variance, p.obs_stddev, p.mean_constant)
+    assert torch.allclose(q.mean.cpu(), m, atol=1e-4)
+    assert torch.allclose(q.scale.to_dense().cpu(), cov, atol=1e-5)
