@@ -58,6 +58,36 @@ _SIGNATURES = {
 
 _lib = None
 
+# Launch accounting: number of kernels of THIS library launched (cuBLAS kernels not counted), and
+# optional CUDA-event timing of the pair kernels on the launching stream (bench.py sets PROFILE = []).
+LAUNCHES = 0
+PROFILE = None
+_KERNELS_PER_CALL = {"cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
+                     "cagp_project_rows": 1, "cagp_gram_mtm": 1, "cagp_assemble_cotangent": 1,
+                     "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1}
+
+
+class _timed:
+    """Counts launches and, when PROFILE is a list, brackets the call with CUDA events."""
+
+    def __init__(self, name, tensor, work=0):
+        self.name, self.tensor, self.work = name, tensor, work
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += _KERNELS_PER_CALL.get(self.name, 1)
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.tensor.device))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream(self.tensor.device))
+            PROFILE.append((self.name, self.e0, self.e1, self.work))
+        return False
+
 
 def lib_path() -> str:
     return _LIB_PATH
@@ -138,7 +168,7 @@ def scale_inputs(family: str, X: torch.Tensor, lengthscale: torch.Tensor) -> tor
     ls = lengthscale.reshape(-1).to(X.dtype).contiguous()
     xs = torch.empty((padded_dim(d), n), dtype=X.dtype, device=X.device)
     kd = make_desc(family, ls, X.dtype)
-    with torch.cuda.device(X.device):
+    with torch.cuda.device(X.device), _timed("cagp_scale_inputs", X, 0):
         _check(load().cagp_scale_inputs(byref(kd), _ptr(X), n, d, _ptr(xs), n, _stream(X)), "cagp_scale_inputs")
     return xs
 
@@ -150,7 +180,7 @@ def ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale) -> torch.Tensor:
     Mt = torch.empty((k, m), dtype=xs1.dtype, device=xs1.device)
     ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype)
-    with torch.cuda.device(xs1.device):
+    with torch.cuda.device(xs1.device), _timed("cagp_ks_blocksparse_fwd", xs1, m * n):
         _check(load().cagp_ks_blocksparse_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Mt), m,
                                               _stream(xs1)), "cagp_ks_blocksparse_fwd")
     return Mt
@@ -167,7 +197,7 @@ def ks_blocksparse_bwd(family, xs1, xs2, d, s, k, Gt, lengthscale):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs1.device)
     s_bar = torch.empty(n, dtype=xs1.dtype, device=xs1.device)
     ls_bar = torch.empty(ls.numel(), dtype=xs1.dtype, device=xs1.device)
-    with torch.cuda.device(xs1.device):
+    with torch.cuda.device(xs1.device), _timed("cagp_ks_blocksparse_bwd", xs1, m * n):
         _check(lib.cagp_ks_blocksparse_bwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Gt),
                                            Gt.shape[1], _ptr(s_bar), _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)),
                "cagp_ks_blocksparse_bwd")
@@ -180,7 +210,7 @@ def project_rows(Mt, row_offset, n_total, s_local, yt_local):
     k, m = Mt.shape
     A = torch.empty((k, k), dtype=Mt.dtype, device=Mt.device)
     c = torch.empty(k, dtype=Mt.dtype, device=Mt.device)
-    with torch.cuda.device(Mt.device):
+    with torch.cuda.device(Mt.device), _timed("cagp_project_rows", Mt, 0):
         _check(load().cagp_project_rows(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(s_local),
                                         _ptr(yt_local), _ptr(A), _ptr(c), _stream(Mt)), "cagp_project_rows")
     return A, c
@@ -190,7 +220,7 @@ def gram_mtm(Mt):
     _require_cuda(Mt)
     k, m = Mt.shape
     B = torch.empty((k, k), dtype=Mt.dtype, device=Mt.device)
-    with torch.cuda.device(Mt.device):
+    with torch.cuda.device(Mt.device), _timed("cagp_gram_mtm", Mt, m * k * k):
         _check(load().cagp_gram_mtm(dtype_code(Mt.dtype), _ptr(Mt), m, m, k, _ptr(B), _stream(Mt)), "cagp_gram_mtm")
     return B
 
@@ -199,7 +229,7 @@ def assemble_cotangent(Mt, row_offset, n_total, W, Abar, cbar, s_local, yt_local
     _require_cuda(Mt, W, Abar, cbar, s_local, yt_local)
     k, m = Mt.shape
     Gt = torch.empty((k, m), dtype=Mt.dtype, device=Mt.device)
-    with torch.cuda.device(Mt.device):
+    with torch.cuda.device(Mt.device), _timed("cagp_assemble_cotangent", Mt, 2 * m * k * k):
         _check(load().cagp_assemble_cotangent(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(W),
                                               _ptr(Abar), _ptr(cbar), _ptr(s_local), _ptr(yt_local), _ptr(Gt), m,
                                               _stream(Mt)), "cagp_assemble_cotangent")
@@ -211,7 +241,7 @@ def project_rows_bwd(Mt, row_offset, n_total, Abar, cbar):
     k, m = Mt.shape
     s_dir = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
     yt_bar = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
-    with torch.cuda.device(Mt.device):
+    with torch.cuda.device(Mt.device), _timed("cagp_project_rows_bwd", Mt, 0):
         _check(load().cagp_project_rows_bwd(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(Abar),
                                             _ptr(cbar), _ptr(s_dir), _ptr(yt_bar), _stream(Mt)),
                "cagp_project_rows_bwd")
@@ -227,7 +257,7 @@ def predict_moments(Mt, w, Pinv, variance, mean_const):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Mt.device)
     mean = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
     var = torch.empty(m, dtype=Mt.dtype, device=Mt.device)
-    with torch.cuda.device(Mt.device):
+    with torch.cuda.device(Mt.device), _timed("cagp_predict_moments", Mt, 0):
         _check(lib.cagp_predict_moments(dtype_code(Mt.dtype), _ptr(Mt), m, m, k, _ptr(w), _ptr(Pinv), _ptr(scalars),
                                         _ptr(mean), _ptr(var), _ptr(ws), ws_bytes, _stream(Mt)),
                "cagp_predict_moments")
