@@ -1,0 +1,90 @@
+"""World-size-2 gloo test of the row-sharding logic (partition, packed all-reduce of the k x k partials
+in the forward, all-reduce of the n-sized cotangents in the backward).  The LOCAL compute is injected:
+here an oracle-backed torch implementation stands in for the native kernels, which need a GPU; the
+plumbing under test (``_fused.ProjectStats`` / ``RowShard``) is the product code."""
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cagpjax_b200 import _fused
+from oracle import cagp_oracle as O
+
+DT = torch.float64
+
+
+def _local_stats(family, X, ls, s, yt, k, shard):
+    """Differentiable local statistics over the rows [begin, end) (oracle arithmetic)."""
+    one = torch.tensor(1.0, dtype=DT)
+    K = O.cross_covariance(family, X[shard.begin:shard.end], X, ls, one)
+    M = O.bds_rmatmat(s, k, K)  # (m, k)
+    blk = O.block_index(shard.n, k)[shard.begin:shard.end]
+    A = torch.zeros(k, k, dtype=DT).index_add(0, blk, s[shard.begin:shard.end, None] * M)
+    return A, M.T @ M, M.T @ yt[shard.begin:shard.end]
+
+
+def oracle_local_fwd(family, X, ls, s, yt, k, shard):
+    with torch.no_grad():
+        A, B, c = _local_stats(family, X, ls, s, yt, k, shard)
+    return A, B, c, None
+
+
+def oracle_local_bwd(family, X, ls, s, yt, k, shard, saved, Abar, Bbar, cbar):
+    with torch.enable_grad():
+        ls_r, s_r, yt_r = (t.detach().clone().requires_grad_(True) for t in (ls, s, yt))
+        A, B, c = _local_stats(family, X, ls_r, s_r, yt_r, k, shard)
+        loss = (A * Abar).sum() + (B * Bbar).sum() + (c * cbar).sum()
+        gl, gs, gy = torch.autograd.grad(loss, [ls_r, s_r, yt_r])
+    return gs, gy[shard.begin:shard.end], gl
+
+
+def _objective(A, B, c):
+    k = A.shape[0]
+    P = A + 0.5 * torch.eye(k, dtype=DT)
+    L = torch.linalg.cholesky(P)
+    return torch.logdet(P) + (torch.cholesky_solve(B, L)).diagonal().sum() + c @ torch.cholesky_solve(c[:, None], L)[:, 0]
+
+
+def _run(shard, family, X, ls, s, yt, k):
+    ls_r, s_r, yt_r = (t.detach().clone().requires_grad_(True) for t in (ls, s, yt))
+    A, B, c = _fused.project_stats(family, X, ls_r, s_r, yt_r, k, shard, None, oracle_local_fwd, oracle_local_bwd)
+    val = _objective(A, B, c)
+    gl, gs, gy = torch.autograd.grad(val, [ls_r, s_r, yt_r])
+    return val.detach(), gl, gs, gy
+
+
+def _worker(rank, world, port, n, d, k, family, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)
+        X = torch.rand(n, d, generator=g, dtype=DT) * 3
+        s = torch.randn(n, generator=g, dtype=DT)
+        yt = torch.randn(n, generator=g, dtype=DT)
+        ls = torch.tensor([0.8, 1.1][:d], dtype=DT)
+        shard = _fused.RowShard.for_rank(n, rank, world, dist.group.WORLD)
+        sharded = _run(shard, family, X, ls, s, yt, k)
+        full = _run(_fused.RowShard.full(n), family, X, ls, s, yt, k)
+        errs = [float((a - b).abs().max() / (b.abs().max() + 1e-300)) for a, b in zip(sharded, full)]
+        out[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,d,k,family", [(157, 2, 6, "rbf"), (64, 1, 8, "matern32")])
+def test_row_sharded_statistics_and_gradients_match_unsharded(n, d, k, family):
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n, d, k, family, out), nprocs=world, join=True)
+    assert set(out.keys()) == {0, 1}
+    for rank in range(world):
+        assert max(out[rank]) < 1e-12, (rank, out[rank])

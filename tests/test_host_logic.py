@@ -1,0 +1,216 @@
+"""CPU tests of the host-side logic: API surface, error behaviour, operator algebra, the C-ABI library
+(loads, exports every declared symbol) and the absence of any CPU fallback on the kernel path."""
+
+import os
+import re
+
+import pytest
+import torch
+
+import cagpjax_b200 as cagp
+from cagpjax_b200 import _fused, _native, gpx, ops
+from cagpjax_b200.linalg import congruence_transform, lower_cholesky
+from cagpjax_b200.linalg.utils import _add_jitter
+from cagpjax_b200.operators import BlockDiagonalSparse, LazyKernel, diag_like
+from cagpjax_b200.operators.annotations import ScaledOrthogonal
+from cagpjax_b200.policies import BlockSparsePolicy
+from cagpjax_b200.solvers import Cholesky
+from oracle import cagp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DT = torch.float64
+
+
+def _rand(*shape, seed=0, dtype=DT):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed), dtype=dtype)
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cagp_b200.h")).read()
+    declared = set(re.findall(r"\b(cagp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cagp_stream_t"}
+    assert declared, "no declarations parsed"
+    lib = _native.load()
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/cagp_b200.h but not exported"
+    assert declared == set(_native.exported_symbols()), "ctypes signatures out of sync with the header"
+    assert lib.cagp_version() >= 100
+    assert [lib.cagp_padded_dim(d) for d in (1, 3, 5, 7, 16, 17, 32, 33)] == [1, 3, 6, 8, 16, 24, 32, -1]
+
+
+def test_no_cpu_fallback_on_kernel_path():
+    x = _rand(20, 2)
+    kernel = gpx.RBF()
+    op = LazyKernel(kernel, x, x)
+    with pytest.raises(_native.NativeLibraryError, match="no CPU fallback"):
+        op @ torch.ones(20, dtype=DT)
+    with pytest.raises(_native.NativeLibraryError, match="no CPU fallback"):
+        (op @ BlockDiagonalSparse(_rand(20), 4)).to_dense()
+
+
+def test_native_argument_errors_are_reported_not_thrown():
+    import ctypes
+
+    lib = _native.load()
+    kd = _native.KernelDesc(7, 1, 1, 0, 0)
+    rc = lib.cagp_scale_inputs(ctypes.byref(kd), None, 10, 2, None, 10, None)
+    assert rc == 1 and b"family" in lib.cagp_last_error_string()
+    assert lib.cagp_project_rows(1, None, 1, 1, 0, 1, 1, None, None, None, None, None) == 1
+
+
+# ---- BlockDiagonalSparse (reference tests/test_operators.py:117-139) ------------------------------
+@pytest.mark.parametrize("shape", [(5, 2), (9, 4), (6, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_block_diagonal_sparse_operator(shape, dtype):
+    n, k = shape
+    nz = _rand(n, dtype=dtype)
+    op = BlockDiagonalSparse(nz, k)
+    assert op.shape == shape and op.dtype == dtype and op.isa(ScaledOrthogonal)
+    mat = op.to_dense()
+    assert torch.equal(mat, O.bds_dense(nz.double(), k).to(dtype))
+    assert torch.allclose(torch.eye(n, dtype=dtype) @ op, mat)
+    assert torch.allclose(op @ torch.eye(k, dtype=dtype), mat)
+    assert op.T.shape == shape[::-1] and torch.allclose(op.T.to_dense(), mat.T)
+    assert (op @ torch.ones(k, dtype=dtype)).dtype == dtype and (op.T @ torch.ones(n, dtype=dtype)).dtype == dtype
+
+
+def test_block_diagonal_sparse_grad():
+    nz = _rand(9).requires_grad_(True)
+    x = _rand(4, seed=1).requires_grad_(True)
+    f = lambda nz, x: torch.prod(torch.sin(BlockDiagonalSparse(nz, 4) @ x))
+    assert torch.autograd.gradcheck(f, (nz, x))
+    y = _rand(9, seed=2).requires_grad_(True)
+    g = lambda nz, y: torch.prod(torch.sin(BlockDiagonalSparse(nz, 4).T @ y))
+    assert torch.autograd.gradcheck(g, (nz, y))
+
+
+# ---- diag_like / congruence / lower_cholesky / jitter (reference tests/test_operators.py:157-180,
+#      tests/test_linalg.py:30-85, 276-416) ---------------------------------------------------------
+def test_diag_like():
+    ref = ops.Dense(torch.ones(5, 5, dtype=torch.float32))
+    a = diag_like(ref, 2.5)
+    assert isinstance(a, ops.ScalarMul) and a.shape == (5, 5) and a.dtype == torch.float32
+    assert torch.allclose(a.to_dense(), 2.5 * torch.eye(5))
+    b = diag_like(ref, torch.arange(1.0, 6.0) ** 2)
+    assert isinstance(b, ops.Diagonal) and torch.allclose(b.to_dense(), torch.diag(torch.arange(1.0, 6.0) ** 2))
+
+
+@pytest.mark.parametrize("n,k", [(7, 3), (10, 2)])
+def test_congruence_overloads(n, k):
+    A = BlockDiagonalSparse(_rand(n), k)
+    B = ops.Diagonal(_rand(n, seed=1))
+    C = congruence_transform(A, B)
+    assert isinstance(C, ops.Diagonal) and C.shape == (k, k)
+    assert torch.allclose(C.to_dense(), A.to_dense().T @ B.to_dense() @ A.to_dense())
+    Cs = congruence_transform(A, ops.ScalarMul(0.3, (n, n), DT))
+    assert isinstance(Cs, ops.Diagonal) and torch.allclose(Cs.to_dense(), 0.3 * A.to_dense().T @ A.to_dense())
+    Dd = congruence_transform(ops.Diagonal(_rand(n)), ops.Diagonal(_rand(n, seed=2)))
+    assert isinstance(Dd, ops.Diagonal)
+    Am, Bm = _rand(n, 3), _rand(n, n, seed=3)
+    assert torch.allclose(congruence_transform(Am, Bm), Am.T @ Bm @ Am)
+    lazy = congruence_transform(ops.Dense(Am), ops.Dense(Bm))
+    assert isinstance(lazy, ops.LinearOperator) and torch.allclose(lazy.to_dense(), Am.T @ Bm @ Am)
+
+
+def test_lower_cholesky_and_jitter_types():
+    d = torch.rand(6, dtype=DT) + 0.5
+    L = lower_cholesky(ops.Diagonal(d), 1e-3)
+    assert isinstance(L, ops.Diagonal) and torch.allclose(L.diag, torch.sqrt(d + 1e-3))
+    L = lower_cholesky(ops.ScalarMul(2.0, (4, 4), DT), 1e-3)
+    assert isinstance(L, ops.ScalarMul) and torch.allclose(torch.as_tensor(L.c), torch.sqrt(torch.tensor(2.001, dtype=DT)))
+    assert isinstance(lower_cholesky(ops.Identity((4, 4), DT)), ops.Identity)
+    R = _rand(5, 5); A = R @ R.T + torch.eye(5, dtype=DT)
+    L = lower_cholesky(ops.Dense(A), 1e-3)
+    assert isinstance(L, ops.Triangular) and torch.allclose(L.A @ L.A.T, A + 1e-3 * torch.eye(5, dtype=DT))
+    assert isinstance(_add_jitter(ops.ScalarMul(1.0, (3, 3), DT), 0.1), ops.ScalarMul)
+    assert isinstance(_add_jitter(ops.Identity((3, 3), DT), 0.1), ops.ScalarMul)
+    assert isinstance(_add_jitter(ops.Diagonal(torch.ones(3, dtype=DT)), 0.1), ops.Diagonal)
+    assert isinstance(_add_jitter(ops.ScalarMul(1.0, (3, 3), DT), torch.ones(3, dtype=DT)), ops.Diagonal)
+    assert isinstance(_add_jitter(ops.Dense(A), 0.1), ops.Sum)
+
+
+# ---- Cholesky solver on small dense operators (reference tests/test_solvers.py) --------------------
+@pytest.mark.parametrize("n", [4, 10])
+def test_cholesky_solver(n):
+    R = _rand(n, n); A = R @ R.T + 0.1 * torch.eye(n, dtype=DT)
+    solver = Cholesky(1e-6)
+    st = solver.init(ops.Dense(A))
+    Aj = A + 1e-6 * torch.eye(n, dtype=DT)
+    b = _rand(n, seed=1)
+    assert torch.allclose(solver.solve(st, b), torch.linalg.solve(Aj, b), rtol=1e-8 * n)
+    assert torch.allclose(solver.logdet(st), torch.linalg.slogdet(Aj)[1])
+    B = _rand(n, 3, seed=2)
+    assert torch.allclose(solver.inv_congruence_transform(st, B), B.T @ torch.linalg.solve(Aj, B))
+    assert torch.allclose(solver.inv_quad(st, b), b @ torch.linalg.solve(Aj, b))
+    other = solver.init(ops.Diagonal(torch.rand(n, dtype=DT) + 0.5))
+    assert torch.allclose(solver.trace_solve(st, other), torch.trace(torch.linalg.solve(Aj, other.to_dense() @ other.to_dense())))
+    z = _rand(n, 2, seed=3)
+    assert torch.allclose(solver.unwhiten(st, z), st.A @ z)
+    with pytest.raises(ValueError, match="jitter must be non-negative"):
+        Cholesky(-1.0)
+
+
+# ---- policies (reference tests/test_policies.py:158-273) -----------------------------------------
+def test_block_sparse_policy():
+    for dtype in (torch.float32, torch.float64):
+        pol = BlockSparsePolicy.from_random(42, 20, 3, dtype=dtype)
+        assert pol.n_actions == 3 and pol.nz_values.shape == (20,) and pol.nz_values.dtype == dtype
+        starts = O.block_starts(20, 3)
+        for b in range(3):
+            assert abs(float(pol.nz_values[starts[b]:starts[b + 1]].norm()) - 1.0) < 1e-6
+    with pytest.raises(ValueError, match="num_datapoints must be at least 1"):
+        BlockSparsePolicy.from_random(0, 0, 3)
+    with pytest.raises(ValueError, match="n_actions must be at least 1"):
+        BlockSparsePolicy(0, torch.ones(3))
+    nz = _rand(10)
+    pol = BlockSparsePolicy(2, gpx.non_trainable(nz))
+    act = pol.to_actions(None)
+    assert isinstance(act, BlockDiagonalSparse) and torch.equal(act.nz_values, nz)
+    assert torch.equal(pol.to_actions(None).to_dense(), pol.to_actions(None, key=3).to_dense())
+    const = BlockSparsePolicy.from_random(1, 12, 2, sampler=lambda key, shape, dtype: torch.full(shape, 3.0, dtype=dtype or DT))
+    assert torch.all(const.nz_values == const.nz_values[0])
+
+
+# ---- LazyKernel host properties (reference tests/test_operators.py:236-260) -----------------------
+@pytest.mark.parametrize("batch_size,max_memory_mb", [(None, 0.0), (None, 32), (9, 32), (27, 0.0)])
+@pytest.mark.parametrize("checkpoint", [True, False])
+def test_lazy_kernel_host_properties(batch_size, max_memory_mb, checkpoint):
+    x1, x2 = _rand(9, 2), _rand(5, 2, seed=1)
+    kernel = gpx.RBF(lengthscale=torch.tensor(1.0, dtype=DT), variance=torch.tensor(1.0, dtype=DT))
+    op = LazyKernel(kernel, x1, x2, batch_size=batch_size, max_memory_mb=max_memory_mb, checkpoint=checkpoint)
+    assert op.shape == (9, 5) and op.dtype == kernel(x1[0], x2[0]).dtype
+    assert op.kernel is kernel and op.x1 is x1 and op.x2 is x2 and op.checkpoint is checkpoint
+    if batch_size is None:
+        if max_memory_mb == 0.0:
+            assert op.batch_size_row == 1 and op.batch_size_col == 1
+        else:
+            assert op.batch_size_row > 1 and op.batch_size_col > 1
+    else:
+        assert op.batch_size_row == batch_size and op.batch_size_col == batch_size
+    assert op.T.shape == (5, 9)
+    eng = cagp.computations.LazyKernelComputation(batch_size=5)
+    g = eng.gram(kernel, x1)
+    assert isinstance(g, LazyKernel) and g.isa(ops.PSDAnnotation) and g.batch_size_row == 5 and g.is_gram
+    c = eng.cross_covariance(kernel, x1, x2)
+    assert isinstance(c, LazyKernel) and not c.is_gram and c.shape == (9, 5)
+
+
+def test_model_requires_supervised_data():
+    kernel = gpx.RBF()
+    model = cagp.ComputationAwareGP(gpx.Prior(kernel, gpx.Zero()) * gpx.Gaussian(10), BlockSparsePolicy.from_random(0, 10, 2))
+    x, y = _rand(10, 1), _rand(10, 1, seed=1)
+    for ds in (gpx.Dataset(None, y), gpx.Dataset(x, None), gpx.Dataset(None, None)):
+        with pytest.raises(ValueError, match="Training data must be supervised"):
+            model.init(ds)
+    assert isinstance(model.solver, Cholesky) and model.solver.jitter == 1e-6
+
+
+def test_row_shard_partition():
+    for n, w in [(10, 3), (1_000_000, 8), (7, 7), (5, 8)]:
+        shards = [_fused.RowShard.for_rank(n, r, w) for r in range(w)]
+        assert shards[0].begin == 0 and shards[-1].end == n
+        assert all(a.end == b.begin for a, b in zip(shards[:-1], shards[1:]))
+        assert max(s.end - s.begin for s in shards) - min(s.end - s.begin for s in shards) <= 1
+    v = _rand(1037)
+    assert torch.allclose(_fused.segment_sum(v, 10), O.congruence_bds_diag(torch.ones(1037, dtype=DT), 10, v))
