@@ -19,6 +19,10 @@ import torch
 
 from . import _native as N
 
+# Gram operators use the symmetric kernels (half the kernel evaluations); False forces the general
+# rectangular kernels (kept for A/B measurements and as the cross-covariance path).
+USE_SYMMETRIC = True
+
 
 # --------------------------------------------------------------------------------------------
 # Row partition / process-group plumbing
@@ -31,6 +35,12 @@ class RowShard:
     end: int
     n: int
     group: object = None  # torch.distributed process group (or None)
+    # block-aligned shards (symmetric Gram path): action blocks [a_begin, a_end) of k, owned by `rank`
+    a_begin: int = -1
+    a_end: int = -1
+    k: int = 0
+    rank: int = 0
+    world: int = 1
 
     @property
     def sharded(self) -> bool:
@@ -39,6 +49,35 @@ class RowShard:
     @staticmethod
     def full(n: int) -> "RowShard":
         return RowShard(0, n, n, None)
+
+    @property
+    def block_aligned(self) -> bool:
+        return self.a_begin >= 0
+
+    @staticmethod
+    def block_range(k: int, rank: int, world: int) -> Tuple[int, int]:
+        base, rem = divmod(k, world)
+        a0 = rank * base + min(rank, rem)
+        return a0, a0 + base + (1 if rank < rem else 0)
+
+    @staticmethod
+    def for_rank_blocks(n: int, k: int, rank: int, world: int, group=None) -> "RowShard":
+        """Shard whose boundaries coincide with action-block boundaries (needs k >= world): rank r owns
+        the action blocks ``block_range(k, r, world)`` and their rows.  The symmetric Gram kernels
+        assign tiles by block, so a rank's tiles produce/consume whole blocks of rows."""
+        if k < world:
+            raise ValueError("block-aligned sharding needs n_actions >= world size")
+        bs = n // k
+        a0, a1 = RowShard.block_range(k, rank, world)
+        begin = a0 * bs
+        end = n if a1 == k else a1 * bs
+        return RowShard(begin, end, n, group, a0, a1, k, rank, world)
+
+    def peer_rows(self, r: int) -> Tuple[int, int]:
+        """Row range of rank r under the same block-aligned partition."""
+        bs = self.n // self.k
+        a0, a1 = RowShard.block_range(self.k, r, self.world)
+        return a0 * bs, (self.n if a1 == self.k else a1 * bs)
 
     @staticmethod
     def for_rank(n: int, rank: int, world: int, group=None) -> "RowShard":
@@ -58,6 +97,70 @@ def _all_reduce_sum(t: torch.Tensor, group) -> torch.Tensor:
     return t
 
 
+def _all_to_all(send: list, recv: list, group) -> None:
+    """recv[r] <- rank r's send[this rank].  NCCL all_to_all; point-to-point on backends without it (gloo)."""
+    import torch.distributed as dist
+
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+        return
+    me = dist.get_rank(group)
+    recv[me].copy_(send[me])
+    ops = []
+    for r in range(dist.get_world_size(group)):
+        if r != me:
+            ops.append(dist.P2POp(dist.isend, send[r], dist.get_global_rank(group, r) if group is not dist.group.WORLD else r, group))
+            ops.append(dist.P2POp(dist.irecv, recv[r], dist.get_global_rank(group, r) if group is not dist.group.WORLD else r, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def exchange_tiles_to_rows(Mfull: torch.Tensor, shard: RowShard) -> torch.Tensor:
+    """Symmetric forward, ranks > 1.  Every rank holds ``Mfull`` (k, n): the entries its own tiles
+    produced, zero elsewhere.  Entry (b, i) is produced by exactly one rank (the owner of blk(i) for
+    row sums, the owner of b for column sums).  Returns the complete local panel Mt (k, rows of this
+    rank): rank h sends block-rows own(h) x columns rows(g) to g, which adds them to its own part."""
+    k, n = Mfull.shape
+    world, me = shard.world, shard.rank
+    a0, a1 = shard.a_begin, shard.a_end
+    send, recv = [], []
+    for r in range(world):
+        r0, r1 = shard.peer_rows(r)
+        send.append(Mfull[a0:a1, r0:r1].contiguous())
+        b0, b1 = RowShard.block_range(k, r, world)
+        recv.append(torch.empty((b1 - b0, shard.end - shard.begin), dtype=Mfull.dtype, device=Mfull.device))
+    _all_to_all(send, recv, shard.group)
+    Mt = Mfull[:, shard.begin:shard.end].contiguous()
+    for r in range(world):
+        if r != me:
+            b0, b1 = RowShard.block_range(k, r, world)
+            Mt[b0:b1] += recv[r]
+    return Mt
+
+
+def gather_cotangent_for_tiles(Gt_local: torch.Tensor, shard: RowShard, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Symmetric backward, ranks > 1.  The tiles (a in own, b) need G[i in own rows, b] (local) and
+    G[j, a in own] for ALL j (remote rows).  Builds a (k, n) buffer holding both: rank h sends the
+    block-rows own(g) of its local panel to g."""
+    k = Gt_local.shape[0]
+    world, me = shard.world, shard.rank
+    a0, a1 = shard.a_begin, shard.a_end
+    Gfull = out if out is not None else torch.empty((k, shard.n), dtype=Gt_local.dtype, device=Gt_local.device)
+    Gfull[:, shard.begin:shard.end] = Gt_local
+    send, recv = [], []
+    for r in range(world):
+        b0, b1 = RowShard.block_range(k, r, world)
+        send.append(Gt_local[b0:b1].contiguous())
+        r0, r1 = shard.peer_rows(r)
+        recv.append(torch.empty((a1 - a0, r1 - r0), dtype=Gt_local.dtype, device=Gt_local.device))
+    _all_to_all(send, recv, shard.group)
+    for r in range(world):
+        if r != me:
+            r0, r1 = shard.peer_rows(r)
+            Gfull[a0:a1, r0:r1] = recv[r]
+    return Gfull
+
+
 # --------------------------------------------------------------------------------------------
 # Local compute (the part that runs native kernels).  Tests for the sharding logic replace this
 # with an oracle-backed callable on CPU (gloo); the product always uses the native one.
@@ -66,8 +169,19 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
     """Returns (A', B', c', Mt, xs): partial statistics over the local rows."""
     d = X.shape[1]
     xs = N.scale_inputs(family, X, lengthscale)
-    xs1 = xs if not shard.sharded and shard.begin == 0 and shard.end == shard.n else xs[:, shard.begin:shard.end].contiguous()
-    Mt = N.ks_blocksparse_fwd(family, xs1, xs, d, s, k, lengthscale)
+    whole = shard.begin == 0 and shard.end == shard.n
+    if whole and USE_SYMMETRIC:
+        # Gram case on one GPU: every kernel value is evaluated once per unordered block pair
+        xs1 = xs
+        Mt = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale)
+    elif shard.block_aligned and USE_SYMMETRIC:
+        xs1 = xs
+        Mfull = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end)
+        Mt = exchange_tiles_to_rows(Mfull, shard)
+        del Mfull
+    else:
+        xs1 = xs if whole else xs[:, shard.begin:shard.end].contiguous()
+        Mt = N.ks_blocksparse_fwd(family, xs1, xs, d, s, k, lengthscale)
     sl = s[shard.begin:shard.end].contiguous()
     yl = yt[shard.begin:shard.end].contiguous()
     A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)
@@ -83,7 +197,15 @@ def native_local_backward(family, X, lengthscale, s, yt, k, shard: RowShard, sav
     yl = yt[shard.begin:shard.end].contiguous()
     W = (Bbar + Bbar.T).contiguous()
     Gt = N.assemble_cotangent(Mt, shard.begin, shard.n, W, Abar.contiguous(), cbar.contiguous(), sl, yl)
-    s_bar, ls_bar = N.ks_blocksparse_bwd(family, xs1, xs, d, s, k, Gt, lengthscale)
+    whole = shard.begin == 0 and shard.end == shard.n
+    if whole and USE_SYMMETRIC:
+        s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale)
+    elif shard.block_aligned and USE_SYMMETRIC:
+        Gfull = gather_cotangent_for_tiles(Gt, shard)
+        s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gfull, lengthscale, shard.a_begin, shard.a_end)
+        del Gfull
+    else:
+        s_bar, ls_bar = N.ks_blocksparse_bwd(family, xs1, xs, d, s, k, Gt, lengthscale)
     del Gt
     s_dir, yt_bar = N.project_rows_bwd(Mt, shard.begin, shard.n, Abar.contiguous(), cbar.contiguous())
     s_bar[shard.begin:shard.end] += s_dir

@@ -40,6 +40,12 @@ _SIGNATURES = {
     "cagp_scale_inputs": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
     "cagp_ks_blocksparse_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                         c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "cagp_ks_blocksparse_fwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
+                                            c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "cagp_ks_bwd_sym_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int32, c_int32, c_int32, c_int32]),
+    "cagp_ks_blocksparse_bwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
+                                            c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_void_p]),
     "cagp_ks_bwd_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int64, c_int32, c_int32]),
     "cagp_ks_blocksparse_bwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                         c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
@@ -62,7 +68,7 @@ _lib = None
 # optional CUDA-event timing of the pair kernels on the launching stream (bench.py sets PROFILE = []).
 LAUNCHES = 0
 PROFILE = None
-_KERNELS_PER_CALL = {"cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
+_KERNELS_PER_CALL = {"cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
                      "cagp_project_rows": 1, "cagp_gram_mtm": 1, "cagp_assemble_cotangent": 1,
                      "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1}
 
@@ -201,6 +207,42 @@ def ks_blocksparse_bwd(family, xs1, xs2, d, s, k, Gt, lengthscale):
         _check(lib.cagp_ks_blocksparse_bwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Gt),
                                            Gt.shape[1], _ptr(s_bar), _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)),
                "cagp_ks_blocksparse_bwd")
+    return s_bar, ls_bar
+
+
+def ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, a_begin=0, a_end=None, out=None) -> torch.Tensor:
+    """Symmetric Gram projection: Mt (k, n) entries of the tiles (a, a+off) for a in [a_begin, a_end)."""
+    _require_cuda(xs, s)
+    n = xs.shape[1]
+    a_end = k if a_end is None else a_end
+    full = a_begin == 0 and a_end == k
+    Mt = out if out is not None else (torch.empty if full else torch.zeros)((k, n), dtype=xs.dtype, device=xs.device)
+    ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
+    kd = make_desc(family, ls, xs.dtype)
+    n_tiles_pairs = n * n // 2 if full else 0
+    with torch.cuda.device(xs.device), _timed("cagp_ks_blocksparse_fwd_sym", xs, n * n if full else 0):
+        _check(load().cagp_ks_blocksparse_fwd_sym(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, _ptr(Mt), n,
+                                                  _stream(xs)), "cagp_ks_blocksparse_fwd_sym")
+    return Mt
+
+
+def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_end=None):
+    """(s_bar (n), ls_bar) contributions of the tiles of blocks [a_begin, a_end), full cotangent Gt (k, n)."""
+    _require_cuda(xs, s, Gt)
+    n = xs.shape[1]
+    a_end = k if a_end is None else a_end
+    ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
+    kd = make_desc(family, ls, xs.dtype)
+    lib = load()
+    ws_bytes = lib.cagp_ks_bwd_sym_ws_bytes(byref(kd), n, d, k, a_begin, a_end)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs.device)
+    s_bar = torch.empty(n, dtype=xs.dtype, device=xs.device)
+    ls_bar = torch.empty(ls.numel(), dtype=xs.dtype, device=xs.device)
+    full = a_begin == 0 and a_end == k
+    with torch.cuda.device(xs.device), _timed("cagp_ks_blocksparse_bwd_sym", xs, n * n if full else 0):
+        _check(lib.cagp_ks_blocksparse_bwd_sym(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, _ptr(Gt),
+                                               Gt.shape[1], _ptr(s_bar), _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs)),
+               "cagp_ks_blocksparse_bwd_sym")
     return s_bar, ls_bar
 
 

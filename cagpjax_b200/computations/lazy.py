@@ -2,7 +2,7 @@
 
 This is the drop-in plug-in point: ``RBF(compute_engine=LazyKernelComputation(...))``.  ``gram``
 returns the PSD-annotated ``LazyKernel(kernel, x, x)`` and ``cross_covariance`` the rectangular
-``LazyKernel(kernel, x1, x2)``, both executed by the sm_100a kernels.  ``row_shard`` (optional)
+``LazyKernel(kernel, x1, x2)``, both executed by the sm_100a kernels.  ``process_group`` (optional)
 partitions the rows of the Gram operator across the ranks of a process group.
 """
 
@@ -10,7 +10,6 @@ from __future__ import annotations
 
 from typing import Optional
 
-from .._fused import RowShard
 from ..gpx import AbstractKernelComputation
 from ..operators import LazyKernel
 from ..ops import PSD
@@ -24,17 +23,9 @@ class LazyKernelComputation(AbstractKernelComputation):
         self.checkpoint = checkpoint
         self.process_group = process_group
 
-    def _shard(self, n: int) -> Optional[RowShard]:
-        if self.process_group is None:
-            return None
-        import torch.distributed as dist
-
-        return RowShard.for_rank(n, dist.get_rank(self.process_group), dist.get_world_size(self.process_group),
-                                 self.process_group)
-
     def gram(self, kernel, x):
         return PSD(LazyKernel(kernel, x, x, batch_size=self.batch_size, max_memory_mb=self.max_memory_mb,
-                              checkpoint=self.checkpoint, row_shard=self._shard(x.shape[0])))
+                              checkpoint=self.checkpoint, process_group=self.process_group))
 
     def cross_covariance(self, kernel, x1, x2):
         return LazyKernel(kernel, x1, x2, batch_size=self.batch_size, max_memory_mb=self.max_memory_mb,

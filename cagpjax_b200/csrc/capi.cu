@@ -10,11 +10,9 @@
 #include <mutex>
 
 #include "aux_kernels.cuh"
-#include "ks_blocksparse.cuh"
-#include "ks_dense.cuh"
-#include "ks_sym.cuh"
+#include "host_common.cuh"
 
-namespace {
+namespace cagp_host {
 
 thread_local char g_err[512] = "";
 
@@ -31,6 +29,23 @@ int check_launch(const char* what) {
     if (e != cudaSuccess) return fail(CAGP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return CAGP_OK;
 }
+
+int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace cagp_host
+
+using namespace cagp_host;
+
+namespace {
 
 // one cuBLAS handle per device, created lazily (the only global state of the library)
 std::mutex g_handle_mu;
@@ -62,189 +77,15 @@ int check_desc(const cagp_kernel_desc* kd, int d) {
     return CAGP_OK;
 }
 
-template <typename F>
-int dispatch_dim(int dp, F&& f) {
-    switch (dp) {
-        case 1: return f(std::integral_constant<int, 1>{});
-        case 2: return f(std::integral_constant<int, 2>{});
-        case 3: return f(std::integral_constant<int, 3>{});
-        case 4: return f(std::integral_constant<int, 4>{});
-        case 6: return f(std::integral_constant<int, 6>{});
-        case 8: return f(std::integral_constant<int, 8>{});
-        case 12: return f(std::integral_constant<int, 12>{});
-        case 16: return f(std::integral_constant<int, 16>{});
-        case 24: return f(std::integral_constant<int, 24>{});
-        case 32: return f(std::integral_constant<int, 32>{});
-    }
-    return fail(CAGP_ERR_UNSUPPORTED, "padded dimension %d not instantiated", dp);
-}
-template <typename F>
-int dispatch_family(int fam, F&& f) {
-    switch (fam) {
-        case CAGP_RBF: return f(std::integral_constant<int, cagp::RBF>{});
-        case CAGP_MATERN12: return f(std::integral_constant<int, cagp::MATERN12>{});
-        case CAGP_MATERN32: return f(std::integral_constant<int, cagp::MATERN32>{});
-        case CAGP_MATERN52: return f(std::integral_constant<int, cagp::MATERN52>{});
-    }
-    return fail(CAGP_ERR_INVALID, "unknown family");
-}
-
-// rows per thread as a function of the (padded) dimension: keep coordinates in registers
-template <int D>
-struct RowsPerThread {
-    static constexpr int value = D <= 4 ? 4 : (D <= 8 ? 2 : 1);
-};
-template <int D>
-struct ColsPerStage {
-    static constexpr int value = D <= 8 ? 256 : 128;
-};
-
-int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
-template <typename T>
-int fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
-             int64_t ld2, int d, const void* s, int k, void* Mt, int64_t ldm, cudaStream_t stream) {
-    const int dp = cagp_padded_dim(d);
-    return dispatch_dim(dp, [&](auto dc) {
-        return dispatch_family(kd->family, [&](auto fc) {
-            constexpr int D = decltype(dc)::value;
-            constexpr int FAM = decltype(fc)::value;
-            constexpr int R = RowsPerThread<D>::value;
-            constexpr int NT = 128;
-            constexpr int JC = ColsPerStage<D>::value;
-            cagp::FwdArgs<T> a;
-            a.xs1 = (const T*)xs1; a.ld1 = ld1; a.m = m;
-            a.xs2 = (const T*)xs2; a.ld2 = ld2;
-            a.s = (const T*)s;
-            a.lay = cagp::BlockLayout{n, k, n / k};
-            a.Mt = (T*)Mt; a.ldm = ldm;
-            const int64_t gx = (m + NT * R - 1) / (NT * R);
-            const int64_t target = (int64_t)num_sms() * 4 * 32;
-            int64_t gy = (target + gx - 1) / gx;
-            if (gy > k) gy = k;
-            if (gy < 1) gy = 1;
-            if (gy > 65535) gy = 65535;
-            a.blocks_per_cta = (int)((k + gy - 1) / gy);
-            gy = (k + a.blocks_per_cta - 1) / a.blocks_per_cta;
-            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
-            auto kern = cagp::ks_fwd_kernel<T, D, FAM, R, NT, JC>;
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
-            return check_launch("ks_fwd_kernel");
-        });
-    });
-}
-
-template <typename T>
-struct BwdPlan {
-    int tiles_main, tiles_last, n_ichunks;
-    int64_t ichunk, gx;
-};
-
-template <typename T, int D>
-BwdPlan<T> plan_bwd(int64_t m, int64_t n, int k) {
-    constexpr int R = RowsPerThread<D>::value;
-    constexpr int NT = 128;
-    cagp::BlockLayout lay{n, k, n / k};
-    BwdPlan<T> pl;
-    pl.tiles_main = (int)((lay.bs + NT * R - 1) / (NT * R));
-    if (pl.tiles_main < 1) pl.tiles_main = 1;
-    pl.tiles_last = (int)((lay.len(k - 1) + NT * R - 1) / (NT * R));
-    if (pl.tiles_last < 1) pl.tiles_last = 1;
-    pl.gx = (int64_t)(k - 1) * pl.tiles_main + pl.tiles_last;
-    const int64_t target = (int64_t)num_sms() * 4 * 32;
-    int64_t gy = (target + pl.gx - 1) / pl.gx;
-    const int64_t max_chunks = (m + 2047) / 2048;  // at least 2048 streamed points per CTA
-    if (gy > max_chunks) gy = max_chunks;
-    if (gy > 64) gy = 64;
-    if (gy < 1) gy = 1;
-    pl.ichunk = (m + gy - 1) / gy;
-    pl.n_ichunks = (int)((m + pl.ichunk - 1) / pl.ichunk);
-    return pl;
-}
-
-template <typename T>
-size_t bwd_ws_bytes(int64_t m, int64_t n, int d, int k, int nls_pad) {
-    // upper bound independent of D: n_ichunks <= 64, gx <= k * ceil(...)
-    const int dp = cagp_padded_dim(d);
-    size_t bytes = 0;
-    dispatch_dim(dp, [&](auto dc) {
-        constexpr int D = decltype(dc)::value;
-        auto pl = plan_bwd<T, D>(m, n, k);
-        bytes = ((size_t)pl.n_ichunks * (size_t)n + (size_t)pl.n_ichunks * (size_t)pl.gx * (size_t)nls_pad) * sizeof(T);
-        return 0;
-    });
-    return bytes + 256;
-}
-
-template <typename T>
-int bwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
-             int64_t ld2, int d, const void* s, int k, const void* Gt, int64_t ldg, void* s_bar, void* ls_bar,
-             void* ws, size_t ws_bytes, cudaStream_t stream) {
-    const int dp = cagp_padded_dim(d);
-    const bool ard = kd->n_lengthscale > 1;
-    return dispatch_dim(dp, [&](auto dc) {
-        return dispatch_family(kd->family, [&](auto fc) {
-            constexpr int D = decltype(dc)::value;
-            constexpr int FAM = decltype(fc)::value;
-            constexpr int R = RowsPerThread<D>::value;
-            constexpr int NT = 128;
-            constexpr int JC = ColsPerStage<D>::value;
-            auto pl = plan_bwd<T, D>(m, n, k);
-            const int nls = ard ? D : 1;
-            const size_t need = ((size_t)pl.n_ichunks * n + (size_t)pl.n_ichunks * pl.gx * nls) * sizeof(T);
-            if (ws_bytes < need) return fail(CAGP_ERR_WORKSPACE, "ks bwd workspace: need %zu bytes, got %zu", need, ws_bytes);
-            cagp::BwdArgs<T> a;
-            a.xs1 = (const T*)xs1; a.ld1 = ld1; a.m = m;
-            a.xs2 = (const T*)xs2; a.ld2 = ld2;
-            a.s = (const T*)s;
-            a.lay = cagp::BlockLayout{n, k, n / k};
-            a.Gt = (const T*)Gt; a.ldg = ldg;
-            a.sbar_part = (T*)ws;
-            a.ls_part = (T*)ws + (size_t)pl.n_ichunks * n;
-            a.tiles_main = pl.tiles_main;
-            a.ichunk = pl.ichunk;
-            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
-            dim3 grid((unsigned)pl.gx, (unsigned)pl.n_ichunks);
-            if (ard) {
-                auto kern = cagp::ks_bwd_kernel<T, D, FAM, true, R, NT, JC>;
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                kern<<<grid, NT, smem, stream>>>(a);
-            } else {
-                auto kern = cagp::ks_bwd_kernel<T, D, FAM, false, R, NT, JC>;
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                kern<<<grid, NT, smem, stream>>>(a);
-            }
-            int rc = check_launch("ks_bwd_kernel");
-            if (rc) return rc;
-            // deterministic reduction of the partials
-            const int64_t nparts = (int64_t)pl.n_ichunks * pl.gx;
-            cagp::bwd_finalize_kernel<T><<<dim3((unsigned)((n + 255) / 256) + 1), 256, 0, stream>>>(
-                a.sbar_part, pl.n_ichunks, n, (T*)s_bar, a.ls_part, nparts, nls, kd->n_lengthscale,
-                (const T*)kd->lengthscale, (T)cagp::family_grad_const(kd->family), (T*)ls_bar);
-            return check_launch("bwd_finalize_kernel");
-        });
-    });
-}
-
 }  // namespace
 
 extern "C" {
 
-const char* cagp_last_error_string(void) { return g_err; }
+const char* cagp_last_error_string(void) { return cagp_host::g_err; }
 int cagp_version(void) { return 100; }
 
 int cagp_padded_dim(int32_t d) {
-    static const int dims[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    static const int dims[] = {1, 2, 3, 4, 8, 16, 32};
     for (int v : dims)
         if (d <= v) return v;
     return -1;
@@ -274,10 +115,37 @@ int cagp_ks_blocksparse_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t
     return fwd_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, s, k, Mt, ldm, (cudaStream_t)stream);
 }
 
+int cagp_ks_blocksparse_fwd_sym(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int32_t d,
+                                const void* s, int32_t k, int32_t a_begin, int32_t a_end, void* Mt, int64_t ldm,
+                                cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs || !s || !Mt) return fail(CAGP_ERR_INVALID, "ks sym fwd: null pointer");
+    if (n < 1 || k < 1 || ld < n || ldm < n || a_begin < 0 || a_end > k || a_begin > a_end) return fail(CAGP_ERR_INVALID, "ks sym fwd: bad shape");
+    if (kd->dtype == CAGP_F64) return sym_fwd_impl<double>(kd, xs, n, ld, d, s, k, a_begin, a_end, Mt, ldm, (cudaStream_t)stream);
+    return sym_fwd_impl<float>(kd, xs, n, ld, d, s, k, a_begin, a_end, Mt, ldm, (cudaStream_t)stream);
+}
+
+size_t cagp_ks_bwd_sym_ws_bytes(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t a_begin, int32_t a_end) {
+    if (check_desc(kd, d) || n < 1 || k < 1) return 0;
+    const bool ard = kd->n_lengthscale > 1;
+    return kd->dtype == CAGP_F64 ? sym_bwd_ws_bytes<double>(n, d, k, ard, a_begin, a_end) : sym_bwd_ws_bytes<float>(n, d, k, ard, a_begin, a_end);
+}
+
+int cagp_ks_blocksparse_bwd_sym(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int32_t d,
+                                const void* s, int32_t k, int32_t a_begin, int32_t a_end, const void* Gt, int64_t ldg,
+                                void* s_bar, void* ls_bar, void* ws, size_t ws_bytes, cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs || !s || !Gt || !s_bar || !ls_bar || !ws) return fail(CAGP_ERR_INVALID, "ks sym bwd: null pointer");
+    if (n < 1 || k < 1 || ld < n || ldg < n || a_begin < 0 || a_end > k || a_begin > a_end) return fail(CAGP_ERR_INVALID, "ks sym bwd: bad shape");
+    if (kd->dtype == CAGP_F64)
+        return sym_bwd_impl<double>(kd, xs, n, ld, d, s, k, a_begin, a_end, Gt, ldg, s_bar, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+    return sym_bwd_impl<float>(kd, xs, n, ld, d, s, k, a_begin, a_end, Gt, ldg, s_bar, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t cagp_ks_bwd_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d, int32_t k) {
     if (check_desc(kd, d) || m < 1 || n < 1 || k < 1) return 0;
-    const int nls = kd->n_lengthscale > 1 ? cagp_padded_dim(d) : 1;
-    return kd->dtype == CAGP_F64 ? bwd_ws_bytes<double>(m, n, d, k, nls) : bwd_ws_bytes<float>(m, n, d, k, nls);
+    const bool ard = kd->n_lengthscale > 1;
+    return kd->dtype == CAGP_F64 ? bwd_ws_bytes<double>(m, n, d, k, ard) : bwd_ws_bytes<float>(m, n, d, k, ard);
 }
 
 int cagp_ks_blocksparse_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2,

@@ -1,0 +1,71 @@
+// Launcher of the symmetric backward kernel (one object per floating-point type).
+#include "aux_kernels.cuh"
+#include "sym_tiling.cuh"
+
+namespace cagp_host {
+
+template <typename T>
+size_t sym_bwd_ws_bytes(int64_t n, int d, int k, bool ard, int a_begin, int a_end) {
+    const int dp = cagp_padded_dim(d);
+    auto til = make_sym_tiling(n, k, a_begin, a_end, sym_rows(n, k, dp, ard));
+    const int64_t gx = sym_grid_x(til);
+    const int gy = sym_choose_groups(til, gx > 0 ? gx : 1);
+    return (size_t)(gx > 0 ? gx : 1) * gy * (ard ? dp : 1) * sizeof(T) + 256;
+}
+
+template <typename T>
+int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int d, const void* s, int k,
+                 int a_begin, int a_end, const void* Gt, int64_t ldg, void* s_bar, void* ls_bar, void* ws,
+                 size_t ws_bytes, cudaStream_t stream) {
+    const int dp = cagp_padded_dim(d);
+    const bool ard = kd->n_lengthscale > 1;
+    const int rows = sym_rows(n, k, dp, ard);
+    return dispatch_dim(dp, [&](auto dc) {
+        return dispatch_family(kd->family, [&](auto fc) {
+            constexpr int D = decltype(dc)::value;
+            constexpr int FAM = decltype(fc)::value;
+            return dispatch_rows<D>(rows, [&](auto rc) {
+                constexpr int R = decltype(rc)::value;
+                constexpr int NT = kSymThreads;
+                constexpr int JC = ColsPerStage<D>::value;
+                auto launch = [&](auto ardc) {
+                    constexpr bool ARD = decltype(ardc)::value;
+                    constexpr int NLS = ARD ? D : 1;
+                    cagp::SymBwdArgs<T> a;
+                    a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Gt = (const T*)Gt; a.ldg = ldg;
+                    a.sbar = (T*)s_bar; a.ls_part = (T*)ws;
+                    a.til = make_sym_tiling(n, k, a_begin, a_end, R);
+                    const int64_t gx = sym_grid_x(a.til);
+                    if (cudaMemsetAsync(s_bar, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset s_bar failed");
+                    int64_t nparts = 0;
+                    if (gx >= 1) {
+                        const int gy = sym_choose_groups(a.til, gx);
+                        nparts = gx * gy;
+                        if (ws_bytes < (size_t)nparts * NLS * sizeof(T)) return fail(CAGP_ERR_WORKSPACE, "ks sym bwd workspace too small");
+                        const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 2 + NT / 32)) * sizeof(T);
+                        auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC>;
+                        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                        if (int rc2 = check_launch("ks_sym_bwd_kernel")) return rc2;
+                    }
+                    cagp::bwd_finalize_kernel<T><<<1, 256, 0, stream>>>(nullptr, 0, 0, nullptr, a.ls_part, nparts, NLS,
+                                                                         kd->n_lengthscale, (const T*)kd->lengthscale,
+                                                                         (T)cagp::family_grad_const(kd->family), (T*)ls_bar);
+                    return check_launch("bwd_finalize_kernel");
+                };
+                // with per-dimension accumulators only R <= MaxRows/2 is instantiated
+                if (ard) {
+                    if constexpr (R <= (MaxRows<D>::value > 1 ? MaxRows<D>::value / 2 : 1)) return launch(std::true_type{});
+                    else return fail(CAGP_ERR_UNSUPPORTED, "ARD backward with %d rows per thread not instantiated", R);
+                }
+                return launch(std::false_type{});
+            });
+        });
+    });
+}
+
+template size_t sym_bwd_ws_bytes<CAGP_REAL>(int64_t, int, int, bool, int, int);
+template int sym_bwd_impl<CAGP_REAL>(const cagp_kernel_desc*, const void*, int64_t, int64_t, int, const void*, int, int,
+                                     int, const void*, int64_t, void*, void*, void*, size_t, cudaStream_t);
+
+}  // namespace cagp_host

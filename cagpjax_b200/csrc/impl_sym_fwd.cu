@@ -1,0 +1,44 @@
+// Launcher of the symmetric forward kernel (one object per floating-point type).
+#include "sym_tiling.cuh"
+
+namespace cagp_host {
+
+template <typename T>
+int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int d, const void* s, int k,
+                 int a_begin, int a_end, void* Mt, int64_t ldm, cudaStream_t stream) {
+    const int dp = cagp_padded_dim(d);
+    const int rows = sym_rows(n, k, dp, false);
+    return dispatch_dim(dp, [&](auto dc) {
+        return dispatch_family(kd->family, [&](auto fc) {
+            constexpr int D = decltype(dc)::value;
+            constexpr int FAM = decltype(fc)::value;
+            return dispatch_rows<D>(rows, [&](auto rc) {
+                constexpr int R = decltype(rc)::value;
+                constexpr int NT = kSymThreads;
+                constexpr int JC = ColsPerStage<D>::value;
+                cagp::SymFwdArgs<T> a;
+                a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Mt = (T*)Mt; a.ldm = ldm;
+                a.til = make_sym_tiling(n, k, a_begin, a_end, R);
+                const int64_t gx = sym_grid_x(a.til);
+                if (gx < 1) return (int)CAGP_OK;
+                const int gy = sym_choose_groups(a.til, gx);
+                // column sums of a block that is split over several CTAs are accumulated atomically
+                if (a.til.tiles_main > 1) {
+                    if (cudaMemsetAsync(Mt, 0, (size_t)k * ldm * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
+                } else if (a.til.tiles_last > 1) {
+                    if (cudaMemsetAsync((T*)Mt + (size_t)(k - 1) * ldm, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
+                }
+                const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NT / 32)) * sizeof(T);
+                auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC>;
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                return check_launch("ks_sym_fwd_kernel");
+            });
+        });
+    });
+}
+
+template int sym_fwd_impl<CAGP_REAL>(const cagp_kernel_desc*, const void*, int64_t, int64_t, int, const void*, int, int,
+                                     int, void*, int64_t, cudaStream_t);
+
+}  // namespace cagp_host

@@ -15,7 +15,7 @@
 // fp64 2^(-u): the fp64 pipe is the roofline of this path (no SFU for doubles), so instead of
 // libm exp (17 fp64 issue slots) we use a 2048-entry table of 2^(-j/2048) staged in shared
 // memory, magic-number range reduction (3 DADD) and a cubic (3 DFMA + 1 DMUL): 7 fp64 slots,
-// max error ~1 ulp.  fp32 uses MUFU.EX2.
+// max error ~1.5 ulp.  fp32 uses MUFU.EX2.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,7 +24,7 @@ namespace cagp {
 
 enum Family : int { RBF = 0, MATERN12 = 1, MATERN32 = 2, MATERN52 = 3 };
 
-constexpr int kExpTabBits = 11;
+constexpr int kExpTabBits = 11;                // 2048 cells of width 2^-11
 constexpr int kExpTabSize = 1 << kExpTabBits;
 
 __device__ const double g_exp2_tab[kExpTabSize] = {
@@ -34,11 +34,19 @@ __device__ const double g_exp2_tab[kExpTabSize] = {
 template <typename T>
 struct ExpTab;
 
+// The table is staged once per CTA in shared memory.  The high word of entry j is stored with the
+// bias + (j << 9) so that the exponent adjustment in exp2neg is a single IMAD.
+// (Measured alternatives, B200, n = 400k, k = 410, d = 3: this 2048-entry table + cubic 1564 Gpairs/s
+//  in the symmetric forward; a 256-entry table replicated 16x to be bank-conflict free + quartic
+//  1508 Gpairs/s - the extra DFMA costs more than the ~5 saved shared-memory wavefronts.)
 template <>
 struct ExpTab<double> {
     static constexpr int kSmemElems = kExpTabSize;
     __device__ static unsigned load(double* tab, int tid, int nthreads) {
-        for (int i = tid; i < kExpTabSize; i += nthreads) tab[i] = g_exp2_tab[i];
+        for (int i = tid; i < kExpTabSize; i += nthreads) {
+            const double v = g_exp2_tab[i];
+            tab[i] = __hiloint2double(__double2hiint(v) + (i << 9), __double2loint(v));
+        }
         return (unsigned)__cvta_generic_to_shared(tab);
     }
 };
@@ -48,33 +56,36 @@ struct ExpTab<float> {
     __device__ static unsigned load(float*, int, int) { return 0u; }
 };
 
-// 2^(-u) for u >= 0 (u may be huge or +inf: the result is then ~2^-1000 ~ 0).
-// `tab_s` is the shared-window address of the 2048-entry table of 2^(-(j + 1/2)/2048)... see below.
+// 2^(-u) for u >= 0 (u huge or +inf gives ~2^-1000 ~ 0).  `tab_s` is the shared-window address of
+// the table (ExpTab<double>::load).
 //
-// magic = 1.5 * 2^38 has ulp 2^-14, so the low mantissa word of t = u + magic is round(u * 2^14)
-// (u < 2^18).  Bits 3..13 of that word index the table (byte offset = lo & 0x3ff8, one LOP3);
-// bits 14.. are the integer part that goes into the exponent.  Clearing bits 0..2 of t and
-// subtracting (magic - 2^-12) gives the centre of the table cell, so f = u - centre lies in
-// [-2^-12, 2^-12] and 2^(-f) is a cubic (Taylor remainder 3.4e-17).
+// magic = 1.5 * 2^41 has ulp 2^-11, so the low mantissa word of t = u + magic is j = round(u * 2048)
+// (u < 2^21; beyond that the high word changes and the result is clamped to ~0).  u = j/2048 + f with
+// |f| <= 2^-12 exactly, hence 2^(-u) = 2^(-(j >> 11)) * T[j & 2047] * 2^(-f): a table value, an
+// exponent adjustment and a cubic in f (Taylor remainder (2^-12 ln2)^4 / 24 = 3.4e-17).
+// fp64 pipe cost: 3 DADD + 3 DFMA + 1 DMUL (libm exp: 17 slots).
 __device__ __forceinline__ double exp2neg(double u, unsigned tab_s) {
-    constexpr double kMagic = 412316860416.0;              // 1.5 * 2^38
-    constexpr double kMagicC = 412316860416.0 - 0x1p-12;   // cell centre offset
-    constexpr int kMagicHi = 0x42580000;                   // high word of kMagic
+    constexpr double kMagic = 3298534883328.0;  // 1.5 * 2^41
+    constexpr int kMagicHi = 0x42880000;        // its high word
     const double t = u + kMagic;
     unsigned lo = (unsigned)__double2loint(t);
     const int hi = __double2hiint(t);
-    const double tc = __hiloint2double(hi, (int)(lo & ~7u));
-    const double f = u - (tc - kMagicC);
+    const double f = u - (t - kMagic);
+    unsigned idx, addr;
+    asm("and.b32 %0, %1, 2047;" : "=r"(idx) : "r"(lo));
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(idx), "r"(tab_s));
     double tv;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(tab_s + (lo & 0x3ff8u)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(addr));
     constexpr double c1 = -0.693147180559945309417232121458;
     constexpr double c2 = 0.240226506959100712333551263163;
     constexpr double c3 = -0.0555041086648215799531422637686;
     const double p = fma(f, fma(f, fma(f, c3, c2), c1), 1.0);
-    // clamp the integer part at 1000 (also when u >= 2^18 spilled into the high word)
+    // clamp the integer part at 1000 (also when u >= 2^21 spilled into the high word)
     lo = (hi == kMagicHi) ? lo : 0xffffffffu;
-    lo = min(lo, 1000u << 14);
-    const int thi = __double2hiint(tv) - (int)((lo & ~0x3fffu) << 6);
+    lo = min(lo, 1000u << kExpTabBits);
+    // table high words carry + (j << 9); subtracting lo << 9 = (n << 20) + (j << 9) leaves 2^-n * T[j]
+    int thi;
+    asm("mad.lo.s32 %0, %1, -512, %2;" : "=r"(thi) : "r"(lo), "r"(__double2hiint(tv)));
     return __hiloint2double(thi, __double2loint(tv)) * p;
 }
 

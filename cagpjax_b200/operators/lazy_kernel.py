@@ -45,7 +45,8 @@ class KernelProjection:
             s = self.actions.nz_values
             yt = self.residual if self.residual is not None else torch.zeros_like(s)
             self._stats = _fused.project_stats(lz.kernel.name, lz.x1, ls, s.contiguous(), yt.contiguous(),
-                                               self.actions.n_blocks, lz.row_shard, self._holder)
+                                               self.actions.n_blocks, lz.row_shard_for(self.actions.n_blocks),
+                                               self._holder)
         return self._stats
 
     @property
@@ -82,7 +83,7 @@ class KernelActions(LinearOperator):
         if self._Mt is None:
             lz = self.lazy
             proj = lz._projections.get(id(self.actions.nz_values))
-            if proj is not None and lz.is_gram and not torch.is_grad_enabled() and not lz.row_shard.sharded:
+            if proj is not None and lz.is_gram and not torch.is_grad_enabled() and lz.process_group is None:
                 self._Mt = proj.Mt
             else:
                 ls, _ = _kernel_params(lz.kernel, lz.x1)
@@ -113,7 +114,7 @@ class LazyKernel(LinearOperator):
     """
 
     def __init__(self, kernel: AbstractKernel, x1: torch.Tensor, x2: torch.Tensor, /, *, max_memory_mb: int = 2**10,
-                 batch_size: Optional[int] = None, checkpoint: bool = False, row_shard: Optional[_fused.RowShard] = None):
+                 batch_size: Optional[int] = None, checkpoint: bool = False, process_group=None):
         shape = (x1.shape[0], x2.shape[0])
         dtype = kernel(x1[0, ...], x2[0, ...]).dtype  # operators/lazy_kernel.py:49
         super().__init__(dtype=dtype, shape=shape, device=x1.device)
@@ -123,8 +124,21 @@ class LazyKernel(LinearOperator):
         self.max_memory_mb = max_memory_mb
         self.batch_size = batch_size
         self.checkpoint = checkpoint
-        self.row_shard = row_shard or _fused.RowShard.full(x1.shape[0])
+        self.process_group = process_group
         self._projections = {}
+
+    def row_shard_for(self, n_blocks: int) -> _fused.RowShard:
+        """Row partition of this (Gram) operator over the ranks of ``process_group``:
+        aligned to action-block boundaries when there are at least as many blocks as ranks."""
+        n = self.shape[0]
+        if self.process_group is None:
+            return _fused.RowShard.full(n)
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+        if n_blocks >= world:
+            return _fused.RowShard.for_rank_blocks(n, n_blocks, rank, world, self.process_group)
+        return _fused.RowShard.for_rank(n, rank, world, self.process_group)
 
     # -- reference batching knobs (operators/lazy_kernel.py:59-77) ---------------------------
     @property

@@ -60,7 +60,7 @@ const char* cagp_last_error_string(void);
 int cagp_version(void);
 
 /* Coordinate dimension the kernels are instantiated for: d is zero-padded up to this value
- * (1, 2, 3, 4, 6, 8, 12, 16, 24, 32); returns -1 if d > 32.  xs buffers have this many rows. */
+ * (1, 2, 3, 4, 8, 16, 32); returns -1 if d > 32.  xs buffers have this many rows. */
 int cagp_padded_dim(int32_t d);
 
 /* xs = scale_and_transpose(X).  Replaces `x / lengthscale` inside the GPJax kernel call made at
@@ -90,6 +90,26 @@ int cagp_ks_blocksparse_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t
                             const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* s,
                             int32_t k, const void* Gt, int64_t ldg, void* s_bar, void* ls_bar,
                             void* ws, size_t ws_bytes, cagp_stream_t stream);
+
+/* Symmetric variants for the Gram case X1 == X2 (kernel.gram, computations/lazy.py:88-106): each
+ * K'(x_i, x_j) is evaluated once per unordered pair of action blocks {a, b} and feeds both
+ * M'[i, b] and M'[j, a].  Tiles are (a, (a + off) mod k), off = 0 .. k/2; [a_begin, a_end) selects the
+ * action blocks a whose tiles this call computes (all blocks: 0, k; a rank's share otherwise).
+ * Mt (k, ldm) with ldm >= n holds ALL n columns: the call writes Mt[b][i in a] and Mt[a][j in b] for
+ * its tiles and leaves the other entries untouched (they belong to other ranks' tiles). */
+int cagp_ks_blocksparse_fwd_sym(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld,
+                                int32_t d, const void* s, int32_t k, int32_t a_begin, int32_t a_end,
+                                void* Mt, int64_t ldm, cagp_stream_t stream);
+
+/* Reverse mode of the symmetric forward for the same tiles, given the FULL cotangent Gt (k, ldg >= n):
+ * s_bar (n) and ls_bar (n_lengthscale) receive this call's tiles' contributions (s_bar is zeroed
+ * first and accumulated with atomics: sums agree to rounding, not bitwise, between runs). */
+size_t cagp_ks_bwd_sym_ws_bytes(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k,
+                                int32_t a_begin, int32_t a_end);
+int cagp_ks_blocksparse_bwd_sym(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld,
+                                int32_t d, const void* s, int32_t k, int32_t a_begin, int32_t a_end,
+                                const void* Gt, int64_t ldg, void* s_bar, void* ls_bar, void* ws,
+                                size_t ws_bytes, cagp_stream_t stream);
 
 /* A'[a][b] = sum_{i in block a} s_i M'[i, b]  (k, k) row-major and c'[b] = sum_i M'[i, b] yt_i,
  * for the m rows held by the caller: global row index of local row i is row_offset + i (row

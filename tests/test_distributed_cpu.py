@@ -88,3 +88,66 @@ def test_row_sharded_statistics_and_gradients_match_unsharded(n, d, k, family):
     assert set(out.keys()) == {0, 1}
     for rank in range(world):
         assert max(out[rank]) < 1e-12, (rank, out[rank])
+
+
+# ---- symmetric Gram path: tile ownership and the two exchanges ----------------------------------------
+def _tile_owner_is_row_block(a: int, b: int, k: int) -> bool:
+    """True if entry (b, i in block a) is a ROW sum of tile (a, b) in the schedule of csrc/ks_sym.cuh."""
+    off = (b - a) % k
+    if off == 0:
+        return True
+    if off > k // 2:
+        return False
+    if 2 * off == k:
+        return a < off
+    return True
+
+
+def _sym_worker(rank, world, port, n, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        Q = torch.randn(k, n, generator=g, dtype=DT)   # the complete M'^T every rank should end up sharing
+        G = torch.randn(k, n, generator=g, dtype=DT)
+        shard = _fused.RowShard.for_rank_blocks(n, k, rank, world, dist.group.WORLD)
+        blk = O.block_index(n, k)
+        owner_of_block = torch.empty(k, dtype=torch.long)
+        for r in range(world):
+            b0, b1 = _fused.RowShard.block_range(k, r, world)
+            owner_of_block[b0:b1] = r
+        # entries of Q this rank's tiles produce
+        mask = torch.zeros(k, n, dtype=torch.bool)
+        for b in range(k):
+            for a in range(k):
+                cols = blk == a
+                row_sum = _tile_owner_is_row_block(a, b, k)
+                producer = owner_of_block[a] if row_sum else owner_of_block[b]
+                if producer == rank:
+                    mask[b, cols] = True
+        Mfull = torch.where(mask, Q, torch.zeros_like(Q))
+        Mt = _fused.exchange_tiles_to_rows(Mfull, shard)
+        ok_fwd = torch.equal(Mt, Q[:, shard.begin:shard.end])
+        Gfull = _fused.gather_cotangent_for_tiles(G[:, shard.begin:shard.end].contiguous(), shard,
+                                                  out=torch.full((k, n), float("nan"), dtype=DT))
+        ok_bwd = torch.equal(Gfull[:, shard.begin:shard.end], G[:, shard.begin:shard.end]) and \
+            torch.equal(Gfull[shard.a_begin:shard.a_end], G[shard.a_begin:shard.a_end])
+        # every entry is produced by exactly one rank
+        cnt = mask.to(torch.int32)
+        dist.all_reduce(cnt)
+        out[rank] = (bool(ok_fwd), bool(ok_bwd), bool((cnt == 1).all()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k,world", [(103, 7, 2), (64, 8, 2), (50, 5, 3)])
+def test_symmetric_tile_exchange(n, k, world):
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sym_worker, args=(world, port, n, k, out), nprocs=world, join=True)
+    for rank in range(world):
+        assert out[rank] == (True, True, True), (rank, out[rank])

@@ -36,7 +36,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"{sym} declared in include/cagp_b200.h but not exported"
     assert declared == set(_native.exported_symbols()), "ctypes signatures out of sync with the header"
     assert lib.cagp_version() >= 100
-    assert [lib.cagp_padded_dim(d) for d in (1, 3, 5, 7, 16, 17, 32, 33)] == [1, 3, 6, 8, 16, 24, 32, -1]
+    assert [lib.cagp_padded_dim(d) for d in (1, 3, 5, 7, 16, 17, 32, 33)] == [1, 3, 8, 8, 16, 32, 32, -1]
 
 
 def test_no_cpu_fallback_on_kernel_path():

@@ -111,3 +111,46 @@ def test_predict_moments(dtype, m=700, k=12):
     mean, v = N.predict_moments(d(Mt), d(w), d(Pinv), d(var), d(mu))
     assert _rel(mean.cpu().numpy(), mean_ref.numpy()) < TOL[dtype] * 5
     assert _rel(v.cpu().numpy(), var_ref.numpy()) < TOL[dtype] * 5
+
+
+SYM_SHAPES = [(9, 1, 4, False), (5, 2, 2, False), (6, 3, 3, True), (1037, 3, 10, False), (1500, 5, 7, True),
+              (2000, 8, 64, False), (777, 16, 5, True), (3, 2, 5, False), (600, 20, 3, False), (4100, 3, 3, False),
+              (2500, 3, 2, True), (64, 2, 64, False), (1000, 1, 1, False)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+@pytest.mark.parametrize("n,d,k,ard", SYM_SHAPES)
+def test_ks_sym_fwd_matches_oracle(dtype, family, n, d, k, ard):
+    x1, x2, s, ls = _data(n, n, d, k, 1, ard)
+    ref = O.projected_kernel_blocksparse(family, x2.numpy(), x2.numpy(), ls.numpy(), s.numpy(), k)
+    X2, S, LS = (t.to(DEV, dtype) for t in (x2, s, ls))
+    xs = N.scale_inputs(family, X2, LS)
+    Mt = N.ks_blocksparse_fwd_sym(family, xs, d, S, k, LS)
+    assert _rel(Mt.T.cpu().numpy(), ref) < TOL[dtype]
+    # a two-"rank" split of the action blocks covers every entry exactly once
+    half = k // 2
+    Ma = N.ks_blocksparse_fwd_sym(family, xs, d, S, k, LS, 0, half)
+    Mb = N.ks_blocksparse_fwd_sym(family, xs, d, S, k, LS, half, k)
+    assert _rel((Ma + Mb).T.cpu().numpy(), ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+@pytest.mark.parametrize("n,d,k,ard", SYM_SHAPES)
+def test_ks_sym_bwd_matches_nonsymmetric(dtype, family, n, d, k, ard):
+    x1, x2, s, ls = _data(n, n, d, k, 2, ard)
+    g = torch.Generator().manual_seed(5)
+    Gt = torch.randn(k, n, generator=g, dtype=torch.float64)
+    X2, S, LS, G = (t.to(DEV, dtype).contiguous() for t in (x2, s, ls, Gt))
+    xs = N.scale_inputs(family, X2, LS)
+    s_ref, l_ref = N.ks_blocksparse_bwd(family, xs, xs, d, S, k, G, LS)  # checked against autograd above
+    s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, S, k, G, LS)
+    tol = TOL[dtype] * 20
+    assert _rel(s_bar.cpu().numpy(), s_ref.cpu().numpy()) < tol
+    assert _rel(ls_bar.cpu().numpy(), l_ref.cpu().numpy()) < tol * 20
+    half = k // 2
+    sa, la = N.ks_blocksparse_bwd_sym(family, xs, d, S, k, G, LS, 0, half)
+    sb, lb = N.ks_blocksparse_bwd_sym(family, xs, d, S, k, G, LS, half, k)
+    assert _rel((sa + sb).cpu().numpy(), s_ref.cpu().numpy()) < tol
+    assert _rel((la + lb).cpu().numpy(), l_ref.cpu().numpy()) < tol * 20

@@ -28,10 +28,10 @@ def timeit(f, reps=3):
     return best
 
 t = timeit(lambda: N.ks_blocksparse_fwd(fam, xs1, xs2, d, s, k, ls))
-print(f"fwd  {fam} {dtype} n={n} m={m} d={d} k={k}: {t:.2f} ms  {m*n/t/1e9:.1f} Gpairs/s")
+print(f"fwd  {fam} {dtype} n={n} m={m} d={d} k={k}: {t:.2f} ms  {m*n/t/1e6:.1f} Gpairs/s")
 Gt = torch.randn(k, m, dtype=dtype, device=dev)
 t = timeit(lambda: N.ks_blocksparse_bwd(fam, xs1, xs2, d, s, k, Gt, ls))
-print(f"bwd  {fam} {dtype} n={n} m={m} d={d} k={k}: {t:.2f} ms  {m*n/t/1e9:.1f} Gpairs/s")
+print(f"bwd  {fam} {dtype} n={n} m={m} d={d} k={k}: {t:.2f} ms  {m*n/t/1e6:.1f} Gpairs/s")
 Mt = N.ks_blocksparse_fwd(fam, xs1, xs2, d, s, k, ls)
 t = timeit(lambda: N.gram_mtm(Mt)); print(f"syrk k={k} m={m}: {t:.2f} ms  {m*k*k/t/1e9:.2f} TFLOP/s (n k^2 flops)")
 W = torch.randn(k, k, dtype=dtype, device=dev); c = torch.randn(k, dtype=dtype, device=dev)
@@ -39,3 +39,7 @@ sl = s[:m].contiguous()
 t = timeit(lambda: N.assemble_cotangent(Mt, 0, n, W, W, c, sl, sl)); print(f"assemble(gemm) : {t:.2f} ms  {2*m*k*k/t/1e9:.2f} TFLOP/s")
 t = timeit(lambda: N.project_rows(Mt, 0, n, sl, sl)); print(f"project_rows: {t:.2f} ms  {Mt.numel()*Mt.element_size()/t/1e6:.0f} GB/s")
 t = timeit(lambda: N.project_rows_bwd(Mt, 0, n, W, c)); print(f"project_rows_bwd: {t:.2f} ms  {Mt.numel()*Mt.element_size()/t/1e6:.0f} GB/s")
+if m == n:
+    t = timeit(lambda: N.ks_blocksparse_fwd_sym(fam, xs2, d, s, k, ls)); print(f"sym fwd: {t:.2f} ms  {n*n/t/1e6:.1f} G(ordered)pairs/s")
+    Gf = torch.randn(k, n, dtype=dtype, device=dev)
+    t = timeit(lambda: N.ks_blocksparse_bwd_sym(fam, xs2, d, s, k, Gf, ls)); print(f"sym bwd: {t:.2f} ms  {n*n/t/1e6:.1f} G(ordered)pairs/s")
