@@ -93,7 +93,8 @@ def _all_reduce_sum(t: torch.Tensor, group) -> torch.Tensor:
         return t
     import torch.distributed as dist
 
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    with N._timed("host:all_reduce", t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
 
@@ -120,6 +121,11 @@ def exchange_tiles_to_rows(Mfull: torch.Tensor, shard: RowShard) -> torch.Tensor
     produced, zero elsewhere.  Entry (b, i) is produced by exactly one rank (the owner of blk(i) for
     row sums, the owner of b for column sums).  Returns the complete local panel Mt (k, rows of this
     rank): rank h sends block-rows own(h) x columns rows(g) to g, which adds them to its own part."""
+    with N._timed("host:exchange_tiles_to_rows", Mfull):
+        return _exchange_tiles_to_rows(Mfull, shard)
+
+
+def _exchange_tiles_to_rows(Mfull: torch.Tensor, shard: RowShard) -> torch.Tensor:
     k, n = Mfull.shape
     world, me = shard.world, shard.rank
     a0, a1 = shard.a_begin, shard.a_end
@@ -142,6 +148,11 @@ def gather_cotangent_for_tiles(Gt_local: torch.Tensor, shard: RowShard, out: Opt
     """Symmetric backward, ranks > 1.  The tiles (a in own, b) need G[i in own rows, b] (local) and
     G[j, a in own] for ALL j (remote rows).  Builds a (k, n) buffer holding both: rank h sends the
     block-rows own(g) of its local panel to g."""
+    with N._timed("host:gather_cotangent_for_tiles", Gt_local):
+        return _gather_cotangent_for_tiles(Gt_local, shard, out)
+
+
+def _gather_cotangent_for_tiles(Gt_local: torch.Tensor, shard: RowShard, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     k = Gt_local.shape[0]
     world, me = shard.world, shard.rank
     a0, a1 = shard.a_begin, shard.a_end

@@ -186,27 +186,26 @@ class ComputationAwareGP:
         """Evidence lower bound: sum of variational expectations minus the prior KL (models/cagp.py:233-249)."""
         if state._projection is not None and isinstance(self.solver, Cholesky) \
                 and isinstance(state.cov_prior_proj_state, Triangular):
-            return self._sum_variational_expectation_fused(state) - self.prior_kl(state)
+            return self._elbo_fused(state)
         return torch.sum(self.variational_expectation(state)) - self.prior_kl(state)
 
     # ------------------------------------------------------------------------------------------
-    def _sum_variational_expectation_fused(self, state: ComputationAwareGPState) -> torch.Tensor:
-        """sum_i E_q[log N(y_i | f_i, sigma^2)] from the k-sized statistics of the fused pass:
-        sum_i var_i = n var - var^2 tr(P^-1 B'),  |y - mean|^2 = |r~|^2 - 2 var w.c' + var^2 w.B'w."""
+    def _elbo_fused(self, state: ComputationAwareGPState) -> torch.Tensor:
+        """ELBO from the k-sized statistics of the fused pass:
+        sum_i var_i = n var - var^2 tr(P^-1 B'),  |y - mean|^2 = |r~|^2 - 2 var w.c' + var^2 w.B'w,
+        minus the KL of ``prior_kl``; evaluated and differentiated in closed form (``_closed_form``)."""
+        from .._closed_form import elbo_from_stats
+        from .._fused import segment_sum
+
         proj = state._projection
         x = torch.atleast_2d(state.train_data.X)
-        n = x.shape[0]
         _, var = _kernel_params(self.posterior.prior.kernel, x)
-        sigma2 = unwrap(self.posterior.likelihood.obs_stddev).to(x.device) ** 2
-        L = state.cov_prior_proj_state.A
-        w = state.repr_weights_proj
-        Bv = var**2 * proj.B
-        cv = var * proj.c
+        sigma = unwrap(self.posterior.likelihood.obs_stddev).to(device=x.device, dtype=var.dtype)
+        nz = state.actions.nz_values
+        q = segment_sum(nz * nz, state.actions.n_blocks)
         yt = state._residual
-        tr = torch.diagonal(torch.cholesky_solve(Bv, L)).sum()
-        sum_var = n * var - tr
-        resid2 = yt @ yt - 2.0 * (w @ cv) + w @ (Bv @ w)
-        return -0.5 * n * (math.log(2.0 * math.pi) + torch.log(sigma2)) - 0.5 * (resid2 + sum_var) / sigma2
+        return elbo_from_stats(proj.A, proj.B, proj.c, state.residual_proj, q, yt @ yt, x.shape[0], var, sigma,
+                               self.solver.jitter)
 
 
 def _kl_divergence_from_solvers(solver, mean_q, cov_q_state, mean_p, cov_p_state) -> torch.Tensor:

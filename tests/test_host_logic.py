@@ -214,3 +214,29 @@ def test_row_shard_partition():
         assert max(s.end - s.begin for s in shards) - min(s.end - s.begin for s in shards) <= 1
     v = _rand(1037)
     assert torch.allclose(_fused.segment_sum(v, 10), O.congruence_bds_diag(torch.ones(1037, dtype=DT), 10, v))
+
+
+# ---- closed-form ELBO on k-sized statistics ---------------------------------------------------------
+@pytest.mark.parametrize("k,n", [(5, 60), (12, 500)])
+def test_closed_form_elbo_matches_autograd_and_oracle(k, n):
+    from cagpjax_b200._closed_form import elbo_from_stats, elbo_from_stats_autograd
+
+    R = _rand(k, k); A = R @ R.T / k
+    M = _rand(n, k, seed=1) * 0.3; yt = _rand(n, seed=2)
+    B, c = M.T @ M, M.T @ yt
+    r, q = _rand(k, seed=3), torch.rand(k, dtype=DT) + 0.5
+    ins = [A, B, c, r, q, yt @ yt, torch.tensor(1.3, dtype=DT), torch.tensor(0.4, dtype=DT)]
+
+    def run(f):
+        xs = [t.clone().requires_grad_(True) for t in ins]
+        v = f(xs[0], xs[1], xs[2], xs[3], xs[4], xs[5], n, xs[6], xs[7], 1e-6)
+        return v.detach(), torch.autograd.grad(v, xs)
+
+    v1, g1 = run(elbo_from_stats_autograd)
+    v2, g2 = run(elbo_from_stats)
+    v3 = O.elbo_from_stats(dict(A=A, B=B, c=c, r=r, q=q, yy=yt @ yt, n=n), 1.3, 0.4, 1e-6)
+    assert torch.allclose(v1, v2, rtol=1e-13) and torch.allclose(v2, v3, rtol=1e-13)
+    for a, b in zip(g1, g2):
+        if a.dim() == 2:
+            a, b = (a + a.T) / 2, (b + b.T) / 2
+        assert torch.allclose(a, b, rtol=1e-10, atol=1e-12 * float(a.abs().max()))
