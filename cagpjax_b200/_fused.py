@@ -325,10 +325,33 @@ def segment_sum(v: torch.Tensor, n_blocks: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # Dense right-hand side: Y = K'(X1, X2) V   (LazyKernel._matmat, operators/lazy_kernel.py:79-90)
 # --------------------------------------------------------------------------------------------
-def kernel_matmat(family: str, X1, X2, lengthscale, V: torch.Tensor) -> torch.Tensor:
-    """K'(X1, X2) @ V for dense V (n, p), differentiable w.r.t. lengthscale and V.
+class KernelMatmat(torch.autograd.Function):
+    """Y = K'(X1, X2) V for dense V (n, p); differentiable w.r.t. lengthscale and V (not X1, X2)."""
 
-    Every column of V is a one-block ``BlockDiagonalSparse`` (k = 1), so the block-sparse kernels
-    compute it exactly; p columns cost p kernel passes."""
-    cols = [ks_matrix(family, X1, X2, lengthscale, V[:, c].contiguous(), 1)[0] for c in range(V.shape[1])]
-    return torch.stack(cols, dim=1)
+    @staticmethod
+    def forward(ctx, X1, X2, lengthscale, V, family):
+        d = X2.shape[1]
+        xs2 = N.scale_inputs(family, X2, lengthscale)
+        same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
+        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale)
+        Vc = V.contiguous()
+        Y = N.ks_dense_fwd(family, xs1, xs2, d, Vc, lengthscale)
+        ctx.family, ctx.d = family, d
+        ctx.save_for_backward(xs1, xs2, Vc, lengthscale)
+        return Y
+
+    @staticmethod
+    def backward(ctx, Ybar):
+        xs1, xs2, V, lengthscale = ctx.saved_tensors
+        Ybar = Ybar.contiguous()
+        V_bar = ls_bar = None
+        if ctx.needs_input_grad[3]:
+            V_bar = N.ks_dense_fwd(ctx.family, xs2, xs1, ctx.d, Ybar, lengthscale)  # K'^T Ybar, K'(x,y) = K'(y,x)
+        if ctx.needs_input_grad[2]:
+            ls_bar = N.ks_dense_bwd_ls(ctx.family, xs1, xs2, ctx.d, V, Ybar, lengthscale).reshape(lengthscale.shape)
+        return None, None, ls_bar, V_bar, None
+
+
+def kernel_matmat(family: str, X1, X2, lengthscale, V: torch.Tensor) -> torch.Tensor:
+    """K'(X1, X2) @ V for dense V (n, p) through the dense sm_100a kernels."""
+    return KernelMatmat.apply(X1, X2, lengthscale, V, family)

@@ -57,6 +57,11 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cagp_project_rows_bwd": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cagp_ks_dense_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
+                                  c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p]),
+    "cagp_ks_dense_bwd_ls_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int64, c_int32]),
+    "cagp_ks_dense_bwd_ls": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
+                                     c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cagp_predict_ws_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "cagp_predict_moments": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -68,7 +73,7 @@ _lib = None
 # optional CUDA-event timing of the pair kernels on the launching stream (bench.py sets PROFILE = []).
 LAUNCHES = 0
 PROFILE = None
-_KERNELS_PER_CALL = {"cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
+_KERNELS_PER_CALL = {"cagp_ks_dense_fwd": 1, "cagp_ks_dense_bwd_ls": 2, "cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
                      "cagp_project_rows": 1, "cagp_gram_mtm": 1, "cagp_assemble_cotangent": 1,
                      "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1}
 
@@ -242,6 +247,35 @@ def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_en
                                                Gt.shape[1], _ptr(s_bar), _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs)),
                "cagp_ks_blocksparse_bwd_sym")
     return s_bar, ls_bar
+
+
+def ks_dense_fwd(family, xs1, xs2, d, V, lengthscale) -> torch.Tensor:
+    """Y (m, p) = K'(X1, X2) V for dense V (n, p)."""
+    _require_cuda(xs1, xs2, V)
+    m, n, p = xs1.shape[1], xs2.shape[1], V.shape[1]
+    Y = torch.empty((m, p), dtype=xs1.dtype, device=xs1.device)
+    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    kd = make_desc(family, ls, xs1.dtype)
+    with torch.cuda.device(xs1.device), _timed("cagp_ks_dense_fwd", xs1, m * n):
+        _check(load().cagp_ks_dense_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(V), p, p, _ptr(Y), p,
+                                        _stream(xs1)), "cagp_ks_dense_fwd")
+    return Y
+
+
+def ks_dense_bwd_ls(family, xs1, xs2, d, V, Ybar, lengthscale) -> torch.Tensor:
+    """ls_bar (n_lengthscale) = sum_ij (Ybar_i . V_j) dK'_ij / d lengthscale."""
+    _require_cuda(xs1, xs2, V, Ybar)
+    m, n, p = xs1.shape[1], xs2.shape[1], V.shape[1]
+    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    kd = make_desc(family, ls, xs1.dtype)
+    lib = load()
+    ws_bytes = lib.cagp_ks_dense_bwd_ls_ws_bytes(byref(kd), m, n, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs1.device)
+    ls_bar = torch.empty(ls.numel(), dtype=xs1.dtype, device=xs1.device)
+    with torch.cuda.device(xs1.device), _timed("cagp_ks_dense_bwd_ls", xs1, m * n):
+        _check(lib.cagp_ks_dense_bwd_ls(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(V), p, _ptr(Ybar), p, p,
+                                        _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)), "cagp_ks_dense_bwd_ls")
+    return ls_bar
 
 
 def project_rows(Mt, row_offset, n_total, s_local, yt_local):

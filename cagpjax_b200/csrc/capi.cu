@@ -238,6 +238,33 @@ int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m,
     return check_launch("project_rows_bwd_kernel");
 }
 
+int cagp_ks_dense_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                      int64_t ld2, int32_t d, const void* V, int32_t p, int64_t ldv, void* Y, int64_t ldy,
+                      cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs1 || !xs2 || !V || !Y) return fail(CAGP_ERR_INVALID, "ks dense fwd: null pointer");
+    if (m < 1 || n < 1 || p < 1 || ld1 < m || ld2 < n || ldv < p || ldy < p) return fail(CAGP_ERR_INVALID, "ks dense fwd: bad shape");
+    if (kd->dtype == CAGP_F64) return dense_fwd_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, V, p, ldv, Y, ldy, (cudaStream_t)stream);
+    return dense_fwd_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, V, p, ldv, Y, ldy, (cudaStream_t)stream);
+}
+
+size_t cagp_ks_dense_bwd_ls_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d) {
+    if (check_desc(kd, d) || m < 1 || n < 1) return 0;
+    const bool ard = kd->n_lengthscale > 1;
+    return kd->dtype == CAGP_F64 ? dense_ls_ws_bytes<double>(m, n, d, ard) : dense_ls_ws_bytes<float>(m, n, d, ard);
+}
+
+int cagp_ks_dense_bwd_ls(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                         int64_t ld2, int32_t d, const void* V, int64_t ldv, const void* Ybar, int64_t ldyb, int32_t p,
+                         void* ls_bar, void* ws, size_t ws_bytes, cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs1 || !xs2 || !V || !Ybar || !ls_bar || !ws) return fail(CAGP_ERR_INVALID, "ks dense bwd: null pointer");
+    if (m < 1 || n < 1 || p < 1 || ld1 < m || ld2 < n || ldv < p || ldyb < p) return fail(CAGP_ERR_INVALID, "ks dense bwd: bad shape");
+    if (kd->dtype == CAGP_F64)
+        return dense_ls_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, V, ldv, Ybar, ldyb, p, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+    return dense_ls_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, V, ldv, Ybar, ldyb, p, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t cagp_predict_ws_bytes(int32_t dtype, int64_t m, int32_t k) {
     const size_t es = dtype == CAGP_F64 ? 8 : 4;
     return (size_t)k * (size_t)m * es;

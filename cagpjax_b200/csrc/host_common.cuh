@@ -86,4 +86,14 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                  int a_begin, int a_end, const void* Gt, int64_t ldg, void* s_bar, void* ls_bar, void* ws,
                  size_t ws_bytes, cudaStream_t stream);
 
+template <typename T>
+int dense_fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                   int64_t ld2, int d, const void* V, int p, int64_t ldv, void* Y, int64_t ldy, cudaStream_t stream);
+template <typename T>
+size_t dense_ls_ws_bytes(int64_t m, int64_t n, int d, bool ard);
+template <typename T>
+int dense_ls_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                  int64_t ld2, int d, const void* V, int64_t ldv, const void* Ybar, int64_t ldyb, int p, void* ls_bar,
+                  void* ws, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace cagp_host

@@ -234,6 +234,8 @@ def _leaf_slots(model) -> List[tuple]:
         slots.append((post.prior.mean_function, "constant"))
     if hasattr(model.policy, "nz_values"):
         slots.append((model.policy, "nz_values"))
+    elif hasattr(model.policy, "actions"):
+        slots.append((model.policy, "actions"))
     return slots
 
 

@@ -1,6 +1,6 @@
 """Linear algebra functions (reference: linalg/__init__.py)."""
 
-from .congruence import ProjectedKernelGram, congruence_transform
+from .congruence import ProjectedDenseGram, ProjectedKernelGram, congruence_transform
 from .lower_cholesky import lower_cholesky
 
-__all__ = ["congruence_transform", "lower_cholesky", "ProjectedKernelGram"]
+__all__ = ["congruence_transform", "lower_cholesky", "ProjectedKernelGram", "ProjectedDenseGram"]

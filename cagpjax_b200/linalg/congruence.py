@@ -6,7 +6,7 @@ import torch
 
 from .. import _fused
 from ..operators import BlockDiagonalSparse, LazyKernel
-from ..ops import Diagonal, LinearOperator, ScalarMul, Sum, diag
+from ..ops import Dense, Diagonal, LinearOperator, ScalarMul, Sum, diag
 
 
 class ProjectedKernelGram(LinearOperator):
@@ -46,6 +46,36 @@ class ProjectedKernelGram(LinearOperator):
         return self
 
 
+class ProjectedDenseGram(LinearOperator):
+    """S^T (K + D) S for a DENSE action matrix S; ``to_dense`` reuses the memoised dense kernel product
+    K S (one 2 n^2 k pass on the GPU) instead of the generic chain of lazy products."""
+
+    def __init__(self, actions: Dense, lazy: LazyKernel, diag_terms):
+        k = actions.shape[1]
+        super().__init__(lazy.dtype, (k, k), device=lazy.device)
+        self.actions = actions
+        self.lazy = lazy
+        self.diag_terms = tuple(diag_terms)
+
+    def to_dense(self) -> torch.Tensor:
+        S = self.actions.A
+        KS = self.lazy.dense_actions(self.actions)
+        out = S.T @ KS.to_dense()
+        for D in self.diag_terms:
+            out = out + S.T @ (D @ S)
+        return out
+
+    def _matmat(self, X):
+        return self.to_dense() @ X
+
+    def _rmatmat(self, X):
+        return X @ self.to_dense()
+
+    @property
+    def T(self):
+        return self
+
+
 def _split_kernel_sum(B):
     """If B = LazyKernel(gram) [+ diagonal-like terms] return (lazy, [diag terms]) else None."""
     if isinstance(B, LazyKernel):
@@ -65,6 +95,7 @@ def congruence_transform(A, B):
       * ``Diagonal, Diagonal`` -> ``Diagonal`` (congruence.py:20-22)
       * ``BlockDiagonalSparse, Diagonal | ScalarMul`` -> ``Diagonal`` by per-block segment sums (:25-43)
       * ``BlockDiagonalSparse, LazyKernel [+ diagonal]`` -> lazy ``ProjectedKernelGram`` (fused CUDA)
+      * ``Dense, LazyKernel [+ diagonal]`` -> lazy ``ProjectedDenseGram`` (dense CUDA kernel product)
       * anything else -> ``A.T @ (B @ A)`` (:15-17)
     """
     if isinstance(A, Diagonal) and isinstance(B, Diagonal):

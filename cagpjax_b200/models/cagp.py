@@ -22,7 +22,7 @@ from ..gpx import ConjugatePosterior, Constant, Dataset, unwrap
 from ..interop import lazify
 from ..linalg import ProjectedKernelGram, congruence_transform
 from ..operators import BlockDiagonalSparse, LazyKernel, diag_like
-from ..operators.lazy_kernel import KernelActions, _kernel_params
+from ..operators.lazy_kernel import KernelActions, KernelDenseActions, _kernel_params
 from ..ops import PSD, LinearOperator, Triangular, diag
 from ..policies import AbstractBatchLinearSolverPolicy
 from ..solvers import AbstractLinearSolver, Cholesky
@@ -41,6 +41,7 @@ class ComputationAwareGPState:
     # B200 additions (not part of the reference state): the fused projection and the residual
     _projection: Any = field(default=None, repr=False)
     _residual: Optional[torch.Tensor] = field(default=None, repr=False)
+    _cov_xx: Any = field(default=None, repr=False)  # the Gram operator of init (memoises K S products)
 
 
 class PredictiveCovariance(LinearOperator):
@@ -82,9 +83,11 @@ class PredictiveCovariance(LinearOperator):
                 return v
             R = torch.linalg.solve_triangular(st.A, var * Mt, upper=False)
             return diag(self.cov_zz) - (R * R).sum(dim=0)
-        KSt = KS.to_dense().T
-        R = self.solver.inv_congruence_transform(self.solver_state, KSt)
-        return diag(self.cov_zz) - torch.diagonal(R)
+        KSt = KS.to_dense().T  # (k, m); never form the m x m product
+        if isinstance(st, Triangular):
+            R = torch.linalg.solve_triangular(st.A, KSt, upper=not st.lower)
+            return diag(self.cov_zz) - (R * R).sum(dim=0)
+        return diag(self.cov_zz) - (KSt * self.solver.solve(st, KSt)).sum(dim=0)
 
 
 class ComputationAwareGP:
@@ -142,7 +145,8 @@ class ComputationAwareGP:
         repr_weights_proj = self.solver.solve(cov_prior_proj_state, residual_proj)
         return ComputationAwareGPState(train_data=train_data, actions=actions, obs_cov_proj=obs_cov_proj,
                                        cov_prior_proj_state=cov_prior_proj_state, residual_proj=residual_proj,
-                                       repr_weights_proj=repr_weights_proj, _projection=projection, _residual=residual)
+                                       repr_weights_proj=repr_weights_proj, _projection=projection, _residual=residual,
+                                       _cov_xx=cov_xx)
 
     def predict(self, state: ComputationAwareGPState, test_inputs: Optional[torch.Tensor] = None) -> GaussianDistribution:
         """Predictive distribution at ``test_inputs`` (training inputs if None) (models/cagp.py:126-169)."""
@@ -153,11 +157,10 @@ class ComputationAwareGP:
         prior = self.posterior.prior
         mean_z = self._mean(z)
         if test_inputs is None:
-            cov_zz = lazify(prior.kernel.gram(x))
+            # same x, same kernel: reuse init's Gram operator so that its memoised K S product
+            # (fused projection / dense product) is not recomputed
+            cov_zz = state._cov_xx if state._cov_xx is not None else lazify(prior.kernel.gram(x))
             cov_zx = cov_zz
-            # reuse the fused projection computed by init (same x, same actions)
-            if state._projection is not None and isinstance(cov_zz, LazyKernel):
-                cov_zz._projections[id(state.actions.nz_values)] = state._projection
         else:
             cov_zz = lazify(prior.kernel.gram(z))
             cov_zx = lazify(prior.kernel.cross_covariance(z, x))

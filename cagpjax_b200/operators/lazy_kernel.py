@@ -16,7 +16,7 @@ import torch
 
 from .. import _fused
 from ..gpx import AbstractKernel, unwrap
-from ..ops import LinearOperator
+from ..ops import Dense, LinearOperator
 from .block_diagonal_sparse import BlockDiagonalSparse
 
 
@@ -104,6 +104,38 @@ class KernelActions(LinearOperator):
         return self._variance() * self.Mt().T
 
 
+class KernelDenseActions(LinearOperator):
+    """Lazy (m, k) operator K(x1, x2) @ S for a DENSE action matrix S (n, k) (cola.ops.Dense actions,
+    SURVEY 8a row a20).  The product M' = K'(x1, x2) S is computed once by the dense sm_100a kernel
+    (2 m n k flops) and shared by init, predict and the ELBO; its reverse mode is two more passes."""
+
+    def __init__(self, lazy: "LazyKernel", actions):
+        super().__init__(lazy.dtype, (lazy.shape[0], actions.shape[1]), device=lazy.device)
+        self.lazy = lazy
+        self.actions = actions
+        self._M = None
+
+    def M(self) -> torch.Tensor:
+        """(m, k) unit-variance product, differentiable w.r.t. lengthscale and the action matrix."""
+        if self._M is None:
+            lz = self.lazy
+            ls, _ = _kernel_params(lz.kernel, lz.x1)
+            self._M = _fused.kernel_matmat(lz.kernel.name, lz.x1, lz.x2, ls, self.actions.A.to(lz.dtype))
+        return self._M
+
+    def _variance(self):
+        return _kernel_params(self.lazy.kernel, self.lazy.x1)[1]
+
+    def _matmat(self, X):
+        return self._variance() * (self.M() @ X)
+
+    def _rmatmat(self, X):
+        return self._variance() * (X @ self.M())
+
+    def to_dense(self):
+        return self._variance() * self.M()
+
+
 class LazyKernel(LinearOperator):
     """K(x1, x2) as a matrix-free operator.
 
@@ -126,6 +158,7 @@ class LazyKernel(LinearOperator):
         self.checkpoint = checkpoint
         self.process_group = process_group
         self._projections = {}
+        self._dense_products = {}
 
     def row_shard_for(self, n_blocks: int) -> _fused.RowShard:
         """Row partition of this (Gram) operator over the ranks of ``process_group``:
@@ -194,7 +227,18 @@ class LazyKernel(LinearOperator):
     def __matmul__(self, other):
         if isinstance(other, BlockDiagonalSparse):
             return KernelActions(self, other)
+        if isinstance(other, Dense):
+            return self.dense_actions(other)
         return super().__matmul__(other)
+
+    def dense_actions(self, actions) -> KernelDenseActions:
+        """K @ S for dense S, memoised per action tensor so that one kernel pass serves every consumer."""
+        key = id(actions.A)
+        op = self._dense_products.get(key)
+        if op is None:
+            op = KernelDenseActions(self, actions)
+            self._dense_products[key] = op
+        return op
 
     def _matmat(self, X: torch.Tensor) -> torch.Tensor:
         """K(x1, x2) @ X for a dense X (n, p) (operators/lazy_kernel.py:79-90)."""

@@ -2,5 +2,6 @@
 
 from .base import AbstractBatchLinearSolverPolicy, AbstractLinearSolverPolicy
 from .block_sparse import BlockSparsePolicy
+from .dense import DensePolicy
 
-__all__ = ["AbstractLinearSolverPolicy", "AbstractBatchLinearSolverPolicy", "BlockSparsePolicy"]
+__all__ = ["AbstractLinearSolverPolicy", "AbstractBatchLinearSolverPolicy", "BlockSparsePolicy", "DensePolicy"]

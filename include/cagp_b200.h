@@ -150,6 +150,24 @@ int cagp_predict_moments(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, 
                          const void* w, const void* Pinv, const void* scalars, void* mean, void* var,
                          void* ws, size_t ws_bytes, cagp_stream_t stream);
 
+/* Dense right-hand side: Y = K'(X1, X2) V with V (n, p) row-major (ldv >= p), Y (m, p) row-major
+ * (ldy >= p).  This is LazyKernel._matmat for a dense operand (operators/lazy_kernel.py:79-90):
+ * matvecs (p = 1) and dense action matrices (cola.ops.Dense actions through the congruence fallback
+ * linalg/congruence.py:15-17).  X @ K (lazy_kernel.py:92-103) is the same call with
+ * xs1 / xs2 swapped, since K'(x, y) = K'(y, x). */
+int cagp_ks_dense_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1,
+                      const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* V, int32_t p,
+                      int64_t ldv, void* Y, int64_t ldy, cagp_stream_t stream);
+
+/* Lengthscale part of the reverse mode of cagp_ks_dense_fwd given Ybar (m, p):
+ *   ls_bar[t] = sum_ij (Ybar_i . V_j) dK'(x1_i, x2_j) / d lengthscale_t.
+ * (The other cotangent, V_bar = K'^T Ybar, is cagp_ks_dense_fwd with xs1 / xs2 swapped.) */
+size_t cagp_ks_dense_bwd_ls_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d);
+int cagp_ks_dense_bwd_ls(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1,
+                         const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* V, int64_t ldv,
+                         const void* Ybar, int64_t ldyb, int32_t p, void* ls_bar, void* ws,
+                         size_t ws_bytes, cagp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,3 +112,37 @@ def test_exact_gp_when_actions_span_everything():
     m, cov = O.exact_gp_predict("rbf", x, y, z, p.lengthscale, p.variance, p.obs_stddev, p.mean_constant)
     assert torch.allclose(q.mean.cpu(), m, atol=1e-4)
     assert torch.allclose(q.scale.to_dense().cpu(), cov, atol=1e-5)
+
+
+@pytest.mark.parametrize("family", ["rbf", "matern52"])
+@pytest.mark.parametrize("n,d,k", [(300, 2, 5), (1100, 16, 32)])
+def test_dense_actions_match_oracle(family, n, d, k):
+    """Dense action matrix (cola.ops.Dense actions; BASELINE config 5 shape) through the same model API."""
+    import cagpjax_b200 as cagp
+    from cagpjax_b200.policies import DensePolicy
+    from tests.util import KERNELS, make_data
+
+    x, y = make_data(n, d, 3, scale=2.0)
+    g = torch.Generator().manual_seed(22)
+    S = torch.randn(n, k, generator=g, dtype=torch.float64) / n**0.5
+    ls = torch.tensor(1.5 if d == 2 else 4.0, dtype=torch.float64)
+    p = O.make_params(ls, 1.3, 0.2, 0.5, S)
+    t = lambda v: torch.as_tensor(v, dtype=torch.float64).to("cuda:0")
+    kernel = KERNELS[family](lengthscale=t(ls), variance=t(1.3))
+    model = cagp.ComputationAwareGP(gpx.Prior(kernel, gpx.Constant(t(0.5))) * gpx.Gaussian(n, obs_stddev=t(0.2)),
+                                    DensePolicy(t(S)))
+    data = gpx.Dataset(t(x), t(y).reshape(-1, 1))
+    with torch.no_grad():
+        st = model.init(data)
+        ost = O.cagp_init(family, x, y, p, None)
+        assert rel_err(st.cov_prior_proj_state.A @ st.cov_prior_proj_state.A.T, ost.L @ ost.L.T) < 1e-10
+        om, ov = O.cagp_predict(family, ost, p)
+        q = model.predict(st)
+        assert rel_err(q.mean, om) < 1e-9 and rel_err(q.variance, ov) < 1e-9
+        assert rel_err(model.prior_kl(st), O.cagp_prior_kl(ost)) < 1e-8
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    oval, ograds = O.elbo_and_grad_literal(family, x, y, p, None)
+    assert rel_err(-val, oval) < 1e-10
+    key_of = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev", "constant": "mean_constant", "actions": "actions"}
+    for name, gval in grads.items():
+        assert rel_err(-gval.reshape(-1), ograds[key_of[name.split(".")[1]]].reshape(-1)) < 1e-7, name

@@ -154,3 +154,28 @@ def test_ks_sym_bwd_matches_nonsymmetric(dtype, family, n, d, k, ard):
     sb, lb = N.ks_blocksparse_bwd_sym(family, xs, d, S, k, G, LS, half, k)
     assert _rel((sa + sb).cpu().numpy(), s_ref.cpu().numpy()) < tol
     assert _rel((la + lb).cpu().numpy(), l_ref.cpu().numpy()) < tol * 20
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+@pytest.mark.parametrize("n,m,d,p,ard", [(9, 5, 2, 1, False), (7, 10, 2, 10, False), (1037, 700, 3, 1, True),
+                                         (900, 1100, 8, 17, False), (2300, 130, 16, 256, True), (700, 700, 5, 300, False),
+                                         (5000, 64, 3, 4, False)])
+def test_ks_dense_fwd_bwd_match_oracle(dtype, family, n, m, d, p, ard):
+    """LazyKernel @ dense (reference tests/test_operators.py:262-313): values and reverse mode."""
+    x1, x2, _, ls = _data(n, m, d, 1, 3, ard)
+    g = torch.Generator().manual_seed(7)
+    V = torch.randn(n, p, generator=g, dtype=torch.float64)
+    Yb = torch.randn(m, p, generator=g, dtype=torch.float64)
+    ls_r, V_r = ls.clone().requires_grad_(True), V.clone().requires_grad_(True)
+    Yref = O.cross_covariance(family, x1, x2, ls_r, torch.tensor(1.0, dtype=torch.float64)) @ V_r
+    gl, gV = torch.autograd.grad((Yref * Yb).sum(), [ls_r, V_r])
+    X1, X2, LS, Vd, Ybd = (t.to(DEV, dtype).contiguous() for t in (x1, x2, ls, V, Yb))
+    xs1, xs2 = N.scale_inputs(family, X1, LS), N.scale_inputs(family, X2, LS)
+    Y = N.ks_dense_fwd(family, xs1, xs2, d, Vd, LS)
+    tol = TOL[dtype] * 10
+    assert _rel(Y.cpu().numpy(), Yref.detach().numpy()) < tol
+    Vbar = N.ks_dense_fwd(family, xs2, xs1, d, Ybd, LS)
+    assert _rel(Vbar.cpu().numpy(), gV.numpy()) < tol
+    lbar = N.ks_dense_bwd_ls(family, xs1, xs2, d, Vd, Ybd, LS)
+    assert _rel(lbar.cpu().numpy(), gl.numpy()) < tol * 50
