@@ -352,6 +352,16 @@ class KernelMatmat(torch.autograd.Function):
         return None, None, ls_bar, V_bar, None
 
 
+# Below this many columns a dense operand is cheaper as p one-block block-sparse passes (the pair
+# kernels run at ~950 Gpairs/s; the GEMM-shaped dense kernel shares one kernel tile across up to 128
+# output columns and only pays off when there are enough of them).
+DENSE_MIN_COLUMNS = 12
+
+
 def kernel_matmat(family: str, X1, X2, lengthscale, V: torch.Tensor) -> torch.Tensor:
-    """K'(X1, X2) @ V for dense V (n, p) through the dense sm_100a kernels."""
+    """K'(X1, X2) @ V for dense V (n, p), differentiable w.r.t. lengthscale and V."""
+    if V.shape[1] < DENSE_MIN_COLUMNS:
+        # every column of V is a one-block BlockDiagonalSparse (k = 1)
+        cols = [ks_matrix(family, X1, X2, lengthscale, V[:, c].contiguous(), 1)[0] for c in range(V.shape[1])]
+        return torch.stack(cols, dim=1)
     return KernelMatmat.apply(X1, X2, lengthscale, V, family)

@@ -272,8 +272,9 @@ def ks_dense_bwd_ls(family, xs1, xs2, d, V, Ybar, lengthscale) -> torch.Tensor:
     ws_bytes = lib.cagp_ks_dense_bwd_ls_ws_bytes(byref(kd), m, n, d)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs1.device)
     ls_bar = torch.empty(ls.numel(), dtype=xs1.dtype, device=xs1.device)
+    Vt, Ybt = V.T.contiguous(), Ybar.T.contiguous()  # point index contiguous for coalesced tile loads
     with torch.cuda.device(xs1.device), _timed("cagp_ks_dense_bwd_ls", xs1, m * n):
-        _check(lib.cagp_ks_dense_bwd_ls(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(V), p, _ptr(Ybar), p, p,
+        _check(lib.cagp_ks_dense_bwd_ls(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(Vt), n, _ptr(Ybt), m, p,
                                         _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)), "cagp_ks_dense_bwd_ls")
     return ls_bar
 

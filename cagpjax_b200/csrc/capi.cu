@@ -259,7 +259,7 @@ int cagp_ks_dense_bwd_ls(const cagp_kernel_desc* kd, const void* xs1, int64_t m,
                          void* ls_bar, void* ws, size_t ws_bytes, cagp_stream_t stream) {
     if (int rc = check_desc(kd, d)) return rc;
     if (!xs1 || !xs2 || !V || !Ybar || !ls_bar || !ws) return fail(CAGP_ERR_INVALID, "ks dense bwd: null pointer");
-    if (m < 1 || n < 1 || p < 1 || ld1 < m || ld2 < n || ldv < p || ldyb < p) return fail(CAGP_ERR_INVALID, "ks dense bwd: bad shape");
+    if (m < 1 || n < 1 || p < 1 || ld1 < m || ld2 < n || ldv < n || ldyb < m) return fail(CAGP_ERR_INVALID, "ks dense bwd: bad shape");
     if (kd->dtype == CAGP_F64)
         return dense_ls_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, V, ldv, Ybar, ldyb, p, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
     return dense_ls_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, V, ldv, Ybar, ldyb, p, ls_bar, ws, ws_bytes, (cudaStream_t)stream);

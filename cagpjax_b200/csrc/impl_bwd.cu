@@ -74,11 +74,11 @@ int bwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
                 dim3 grid((unsigned)pl.gx, (unsigned)pl.n_ichunks);
                 if (ard) {
                     auto kern = cagp::ks_bwd_kernel<T, D, FAM, true, R, NT, JC>;
-                    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     kern<<<grid, NT, smem, stream>>>(a);
                 } else {
                     auto kern = cagp::ks_bwd_kernel<T, D, FAM, false, R, NT, JC>;
-                    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     kern<<<grid, NT, smem, stream>>>(a);
                 }
                 if (int rc2 = check_launch("ks_bwd_kernel")) return rc2;

@@ -34,7 +34,7 @@ int dense_fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64
             }
             const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)cagp::kDenseJC * (D + cagp::kDenseRows + cagp::kDenseCols)) * sizeof(T);
             auto kern = cagp::ks_dense_fwd_kernel<T, D, FAM>;
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), cagp::kDenseThreads, smem, stream>>>(a);
             return check_launch("ks_dense_fwd_kernel");
         });
@@ -85,12 +85,13 @@ int dense_ls_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_
                 cagp::DenseLsArgs<T> a;
                 a.xs1 = (const T*)xs1; a.ld1 = ld1; a.m = m;
                 a.xs2 = (const T*)xs2; a.ld2 = ld2; a.n = n;
-                a.Ybar = (const T*)Ybar; a.ldyb = ldyb;
-                a.V = (const T*)V; a.ldv = ldv; a.p = p;
+                a.Ybt = (const T*)Ybar; a.ldyb = ldyb;
+                a.Vt = (const T*)V; a.ldv = ldv; a.p = p;
                 a.ls_part = (T*)ws;
                 a.jchunk = pl.jchunk;
-                const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)16 * 128) * sizeof(T);
+                const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)32 * 128) * sizeof(T);
                 auto kern = cagp::ks_dense_bwd_ls_kernel<T, D, FAM, ARD>;
+                if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 kern<<<dim3((unsigned)pl.gx, (unsigned)pl.gy), 128, smem, stream>>>(a);
                 if (int rc = check_launch("ks_dense_bwd_ls_kernel")) return rc;
                 cagp::bwd_finalize_kernel<T><<<1, 256, 0, stream>>>(nullptr, 0, 0, nullptr, a.ls_part, nparts, NLS,

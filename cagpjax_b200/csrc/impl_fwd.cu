@@ -31,7 +31,7 @@ int fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
             gy = (k + a.blocks_per_cta - 1) / a.blocks_per_cta;
             const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
             auto kern = cagp::ks_fwd_kernel<T, D, FAM, R, NT, JC>;
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
             return check_launch("ks_fwd_kernel");
         });

@@ -44,7 +44,7 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                         if (ws_bytes < (size_t)nparts * NLS * sizeof(T)) return fail(CAGP_ERR_WORKSPACE, "ks sym bwd workspace too small");
                         const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 2 + NT / 32)) * sizeof(T);
                         auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC>;
-                        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                         kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
                         if (int rc2 = check_launch("ks_sym_bwd_kernel")) return rc2;
                     }

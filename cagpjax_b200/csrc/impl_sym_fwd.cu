@@ -30,7 +30,7 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 }
                 const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NT / 32)) * sizeof(T);
                 auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC>;
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
                 return check_launch("ks_sym_fwd_kernel");
             });

@@ -45,7 +45,7 @@ __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
 }
 
 template <typename T, int D, int FAM>
-__global__ void __launch_bounds__(kDenseThreads) ks_dense_fwd_kernel(const DenseFwdArgs<T> p) {
+__global__ void __launch_bounds__(kDenseThreads, 2) ks_dense_fwd_kernel(const DenseFwdArgs<T> p) {
     constexpr int JC = kDenseJC, TM = kDenseRows, TP = kDenseCols;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
@@ -133,15 +133,16 @@ template <typename T>
 struct DenseLsArgs {
     const T* xs1; int64_t ld1; int64_t m;
     const T* xs2; int64_t ld2; int64_t n;
-    const T* Ybar; int64_t ldyb;
-    const T* V; int64_t ldv; int p;
+    const T* Ybt; int64_t ldyb;  // Ybar transposed: (p, m)
+    const T* Vt; int64_t ldv;    // V transposed: (p, n)
+    int p;
     T* ls_part;  // [gridDim.y * gridDim.x][NLS]
     int64_t jchunk;
 };
 
 template <typename T, int D, int FAM, bool ARD>
-__global__ void __launch_bounds__(128) ks_dense_bwd_ls_kernel(const DenseLsArgs<T> p) {
-    constexpr int TM = 64, TN = 64, PC = 16, NLS = ARD ? D : 1;
+__global__ void __launch_bounds__(128, 3) ks_dense_bwd_ls_kernel(const DenseLsArgs<T> p) {
+    constexpr int TM = 64, TN = 64, PC = 32, NLS = ARD ? D : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
     T* Ys = tab + ExpTab<T>::kSmemElems;  // [PC][TM]
@@ -165,11 +166,11 @@ __global__ void __launch_bounds__(128) ks_dense_bwd_ls_kernel(const DenseLsArgs<
         for (int c0 = 0; c0 < p.p; c0 += PC) {
             __syncthreads();
             for (int idx = tid; idx < PC * TM; idx += 128) {
-                const int ii = idx / PC, cc = idx % PC;  // coalesced along the p axis
+                const int cc = idx / TM, ii = idx % TM;  // coalesced along the point axis (transposed operands)
                 const int64_t gi = i0 + ii;
-                Ys[cc * TM + ii] = (gi < p.m && c0 + cc < p.p) ? p.Ybar[gi * p.ldyb + c0 + cc] : T(0);
+                Ys[idx] = (gi < p.m && c0 + cc < p.p) ? p.Ybt[(int64_t)(c0 + cc) * p.ldyb + gi] : T(0);
                 const int64_t gj = j0 + ii;
-                Vs[cc * TN + ii] = (gj < j_end && c0 + cc < p.p) ? p.V[gj * p.ldv + c0 + cc] : T(0);
+                Vs[idx] = (gj < j_end && c0 + cc < p.p) ? p.Vt[(int64_t)(c0 + cc) * p.ldv + gj] : T(0);
             }
             __syncthreads();
 #pragma unroll 4

@@ -159,13 +159,15 @@ int cagp_ks_dense_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, in
                       const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* V, int32_t p,
                       int64_t ldv, void* Y, int64_t ldy, cagp_stream_t stream);
 
-/* Lengthscale part of the reverse mode of cagp_ks_dense_fwd given Ybar (m, p):
+/* Lengthscale part of the reverse mode of cagp_ks_dense_fwd given the cotangent Ybar (m, p):
  *   ls_bar[t] = sum_ij (Ybar_i . V_j) dK'(x1_i, x2_j) / d lengthscale_t.
+ * Both dense operands are passed TRANSPOSED (point index contiguous): Vt (p, ldv >= n) and
+ * Ybt (p, ldyb >= m), so that tile loads are coalesced.
  * (The other cotangent, V_bar = K'^T Ybar, is cagp_ks_dense_fwd with xs1 / xs2 swapped.) */
 size_t cagp_ks_dense_bwd_ls_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d);
 int cagp_ks_dense_bwd_ls(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1,
-                         const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* V, int64_t ldv,
-                         const void* Ybar, int64_t ldyb, int32_t p, void* ls_bar, void* ws,
+                         const void* xs2, int64_t n, int64_t ld2, int32_t d, const void* Vt, int64_t ldv,
+                         const void* Ybt, int64_t ldyb, int32_t p, void* ls_bar, void* ws,
                          size_t ws_bytes, cagp_stream_t stream);
 
 #ifdef __cplusplus

@@ -146,3 +146,34 @@ def test_dense_actions_match_oracle(family, n, d, k):
     key_of = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev", "constant": "mean_constant", "actions": "actions"}
     for name, gval in grads.items():
         assert rel_err(-gval.reshape(-1), ograds[key_of[name.split(".")[1]]].reshape(-1)) < 1e-7, name
+
+
+@pytest.mark.parametrize("n,dtype", [(20_000, torch.float64), (40_000, torch.float32)])
+def test_large_lazy_kernel_matvec_with_grad(n, dtype):
+    """Reference tests/test_operators.py:275-313: loss = v . (K(x1, x2) v), finite, reverse-mode gradient
+    w.r.t. the kernel parameters against central finite differences (rtol 1e-6 f64 / 1e-2 f32)."""
+    from cagpjax_b200.operators import LazyKernel
+
+    g = torch.Generator().manual_seed(42)
+    x1 = torch.randn(n, 2, generator=g, dtype=torch.float64).to("cuda:0", dtype)
+    x2 = torch.randn(n, 2, generator=g, dtype=torch.float64).to("cuda:0", dtype)
+    v = torch.randn(n, generator=g, dtype=torch.float64).to("cuda:0", dtype)
+    ls0, var0 = torch.rand(2, generator=g, dtype=torch.float64).tolist()
+
+    def loss(ls, var):
+        kernel = gpx.RBF(lengthscale=ls, variance=var)
+        return torch.dot(v, LazyKernel(kernel, x1, x2, max_memory_mb=2**8, checkpoint=True) @ v)
+
+    ls = torch.tensor(ls0, dtype=dtype, device="cuda:0", requires_grad=True)
+    var = torch.tensor(var0, dtype=dtype, device="cuda:0", requires_grad=True)
+    val = loss(ls, var)
+    assert torch.isfinite(val)
+    gl, gv = torch.autograd.grad(val, [ls, var])
+    h = 1e-6 if dtype == torch.float64 else 1e-2
+    rtol = 1e-6 if dtype == torch.float64 else 1e-2
+    with torch.no_grad():
+        c = lambda v_: torch.tensor(v_, dtype=dtype, device="cuda:0")
+        fd_l = (loss(c(ls0 + h), c(var0)) - loss(c(ls0 - h), c(var0))) / (2 * h)
+        fd_v = (loss(c(ls0), c(var0 + h)) - loss(c(ls0), c(var0 - h))) / (2 * h)
+    assert abs(float(gl - fd_l)) <= rtol * abs(float(fd_l)) + (1e-6 if dtype == torch.float64 else 1.0)
+    assert abs(float(gv - fd_v)) <= rtol * abs(float(fd_v)) + (1e-6 if dtype == torch.float64 else 1.0)
