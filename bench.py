@@ -32,6 +32,8 @@ CONFIGS = {
     # name: (n, d, family, k, dtype)
     "c1": dict(n=1000, d=1, family="rbf", k=10, dtype="f64", desc="README example shape n=1000,d=1,RBF,k=10"),
     "c2": dict(n=100_000, d=8, family="matern32", k=512, dtype="f64", desc="n=100k,d=8,Matern-3/2,k=512"),
+    # profiling-size variant of c3: same block size (976 rows per action block), 1/16 of the pairs
+    "c3s": dict(n=250_000, d=3, family="rbf", k=256, dtype="f64", desc="n=250k,d=3,RBF,BlockSparse k=256,float64 (c3 block size, ncu-sized)"),
     "c3": dict(n=1_000_000, d=3, family="rbf", k=1024, dtype="f64", desc="n=1M,d=3,RBF,BlockSparse k=1024,float64"),
 }
 
@@ -42,6 +44,11 @@ def pair_flops(family: str, d: int, backward: bool) -> int:
 
 
 FP64_PEAK_TFLOPS = 33.9  # measured DFMA stream on this pool's B200 (profiles/r01_fp64_peaks.json); nominal 37.2
+
+# fp64 issue slots actually executed per ORDERED pair by each pair kernel (counted in the SASS of the
+# d = 3 RBF instances; the symmetric kernels evaluate each unordered pair once = half per ordered pair).
+FP64_SLOTS_PER_PAIR = {"cagp_ks_blocksparse_fwd": 14.0, "cagp_ks_blocksparse_bwd": 16.0,
+                       "cagp_ks_blocksparse_fwd_sym": 7.5, "cagp_ks_blocksparse_bwd_sym": 9.0}
 
 
 def synth(cfg, device, dtype):
@@ -256,8 +263,10 @@ def main():
     achieved = flops / (kern_ms[dom] * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
-                "note": "declared algorithmic flops (libm-exp cost model, SURVEY 8d) / CUDA-event kernel time; peak = measured DFMA stream (of measured; nominal 37.2)",
+                "note": "achieved = declared algorithmic flops (libm-exp cost model, SURVEY 8d: 3d+34 fwd / 3d+40 bwd per ordered pair) / CUDA-event kernel time; peak = measured DFMA stream (of measured; nominal 37.2). frac > 1 because the kernels spend fewer fp64 slots than the declared model (table-based exp2, symmetric tiles); fp64_pipe_frac = executed fp64 slots x 2 / time / peak is the pipe utilisation",
                 "pairs_per_sec": pairs_per_launch / (kern_ms[dom] * 1e-3),
+                "fp64_pipe_frac": (pairs_per_launch / (kern_ms[dom] * 1e-3)) * FP64_SLOTS_PER_PAIR.get(dom, 0.0) * 2.0 / 1e12 / FP64_PEAK_TFLOPS
+                if (fam == "rbf" and dd == 3 and cfg["dtype"] == "f64") else None,
                 "kernel_ms": {nm: round(v, 3) for nm, v in kern_ms.items()}}
 
     # end-to-end: host buffers -> device, step, gradients -> host, every step
