@@ -179,7 +179,7 @@ def _gather_cotangent_for_tiles(Gt_local: torch.Tensor, shard: RowShard, out: Op
 def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
     """Returns (A', B', c', Mt, xs): partial statistics over the local rows."""
     d = X.shape[1]
-    xs = N.scale_inputs(family, X, lengthscale)
+    xs = N.scale_inputs(family, X, lengthscale, X[0])
     whole = shard.begin == 0 and shard.end == shard.n
     if whole and USE_SYMMETRIC:
         # Gram case on one GPU: every kernel value is evaluated once per unordered block pair
@@ -280,9 +280,9 @@ class KSMatrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X1, X2, lengthscale, s, family, k):
         d = X2.shape[1]
-        xs2 = N.scale_inputs(family, X2, lengthscale)
+        xs2 = N.scale_inputs(family, X2, lengthscale, X2[0])
         same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
-        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale)
+        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale, X2[0])
         Mt = N.ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale)
         ctx.family, ctx.k, ctx.d = family, k, d
         ctx.save_for_backward(xs1, xs2, s, lengthscale)
@@ -331,9 +331,9 @@ class KernelMatmat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X1, X2, lengthscale, V, family):
         d = X2.shape[1]
-        xs2 = N.scale_inputs(family, X2, lengthscale)
+        xs2 = N.scale_inputs(family, X2, lengthscale, X2[0])
         same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
-        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale)
+        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale, X2[0])
         Vc = V.contiguous()
         Y = N.ks_dense_fwd(family, xs1, xs2, d, Vc, lengthscale)
         ctx.family, ctx.d = family, d

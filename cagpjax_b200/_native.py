@@ -37,7 +37,7 @@ _SIGNATURES = {
     "cagp_last_error_string": (c_char_p, []),
     "cagp_version": (c_int, []),
     "cagp_padded_dim": (c_int, [c_int32]),
-    "cagp_scale_inputs": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
+    "cagp_scale_inputs": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "cagp_ks_blocksparse_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                         c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "cagp_ks_blocksparse_fwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
@@ -172,15 +172,19 @@ def padded_dim(d: int) -> int:
     return v
 
 
-def scale_inputs(family: str, X: torch.Tensor, lengthscale: torch.Tensor) -> torch.Tensor:
-    """xs (padded_dim(d), n): scaled, transposed inputs."""
+def scale_inputs(family: str, X: torch.Tensor, lengthscale: torch.Tensor, origin: torch.Tensor = None) -> torch.Tensor:
+    """xs (padded_dim(d), n): inputs shifted by ``origin`` (d,), scaled and transposed."""
     _require_cuda(X, lengthscale)
     n, d = X.shape
+    if origin is not None:
+        origin = origin.detach().reshape(-1).to(X.dtype).contiguous()
+        _require_cuda(origin)
     ls = lengthscale.reshape(-1).to(X.dtype).contiguous()
     xs = torch.empty((padded_dim(d), n), dtype=X.dtype, device=X.device)
     kd = make_desc(family, ls, X.dtype)
     with torch.cuda.device(X.device), _timed("cagp_scale_inputs", X, 0):
-        _check(load().cagp_scale_inputs(byref(kd), _ptr(X), n, d, _ptr(xs), n, _stream(X)), "cagp_scale_inputs")
+        _check(load().cagp_scale_inputs(byref(kd), _ptr(X), n, d, _ptr(origin) if origin is not None else None, _ptr(xs),
+                                        n, _stream(X)), "cagp_scale_inputs")
     return xs
 
 

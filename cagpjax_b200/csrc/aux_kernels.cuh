@@ -12,17 +12,18 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-// xs[t*ld + i] = X[i*d + t] * c / lengthscale_t for t < d, 0 for d <= t < gridDim.y (padding)
+// xs[t*ld + i] = (X[i*d + t] - origin[t]) * c / lengthscale_t for t < d, 0 for d <= t < gridDim.y (padding)
 template <typename T>
 __global__ void scale_inputs_kernel(const T* __restrict__ X, int64_t n, int d, const T* __restrict__ ls, int n_ls, T c,
-                                    T* __restrict__ xs, int64_t ld) {
+                                    const T* __restrict__ origin, T* __restrict__ xs, int64_t ld) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
     if (i >= n) return;
     T v = T(0);
     if (t < d) {
         const T l = ls[n_ls > 1 ? t : 0];
-        v = X[i * d + t] * (c / l);
+        const T o = origin ? origin[t] : T(0);
+        v = (X[i * d + t] - o) * (c / l);
     }
     xs[(int64_t)t * ld + i] = v;
 }

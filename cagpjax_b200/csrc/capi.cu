@@ -91,17 +91,17 @@ int cagp_padded_dim(int32_t d) {
     return -1;
 }
 
-int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d, void* xs, int64_t ld,
-                      cagp_stream_t stream) {
+int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d, const void* origin, void* xs,
+                      int64_t ld, cagp_stream_t stream) {
     if (int rc = check_desc(kd, d)) return rc;
     if (!X || !xs || n < 1 || ld < n) return fail(CAGP_ERR_INVALID, "scale_inputs: bad X/xs/n/ld");
     const int dp = cagp_padded_dim(d);
     const double c = cagp::family_scale(kd->family);
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)dp);
     if (kd->dtype == CAGP_F64)
-        cagp::scale_inputs_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)X, n, d, (const double*)kd->lengthscale, kd->n_lengthscale, c, (double*)xs, ld);
+        cagp::scale_inputs_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)X, n, d, (const double*)kd->lengthscale, kd->n_lengthscale, c, (const double*)origin, (double*)xs, ld);
     else
-        cagp::scale_inputs_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, n, d, (const float*)kd->lengthscale, kd->n_lengthscale, (float)c, (float*)xs, ld);
+        cagp::scale_inputs_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, n, d, (const float*)kd->lengthscale, kd->n_lengthscale, (float)c, (const float*)origin, (float*)xs, ld);
     return check_launch("scale_inputs_kernel");
 }
 

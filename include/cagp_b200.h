@@ -14,7 +14,7 @@
  *
  * Data layout conventions
  *   X       row-major (n, d) inputs exactly as the reference holds them (cagp.py:91).
- *   xs      "scaled SoA" copy, shape (d, ld): xs[t*ld + i] = X[i*d + t] * c_family / lengthscale_t.
+ *   xs      "scaled SoA" copy, shape (d, ld): xs[t*ld + i] = (X[i*d + t] - origin_t) * c_family / lengthscale_t.
  *           c_family folds the kernel's exponent constant and log2(e) so that the kernels
  *           evaluate 2^(-q) (RBF) or 2^(-sqrt q) (Matern) on q = sum_t (xs1_t - xs2_t)^2.
  *   Mt      the projected kernel matrix M' = K'(X1, X2) S stored k-major: Mt[b*ld + i] = M'[i, b]
@@ -63,10 +63,13 @@ int cagp_version(void);
  * (1, 2, 3, 4, 8, 16, 32); returns -1 if d > 32.  xs buffers have this many rows. */
 int cagp_padded_dim(int32_t d);
 
-/* xs = scale_and_transpose(X).  Replaces `x / lengthscale` inside the GPJax kernel call made at
- * operators/lazy_kernel.py:83-85.  X (n, d) row-major; xs (cagp_padded_dim(d), ld), ld >= n; padding rows are zeroed. */
-int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d, void* xs,
-                      int64_t ld, cagp_stream_t stream);
+/* xs = scale_and_transpose(X - origin).  Replaces `x / lengthscale` inside the GPJax kernel call made
+ * at operators/lazy_kernel.py:83-85.  X (n, d) row-major; xs (cagp_padded_dim(d), ld), ld >= n; padding
+ * rows are zeroed.  `origin` (device pointer, d elements, or NULL) is subtracted before scaling: stationary
+ * kernels only see differences, and removing a common offset keeps those differences accurate for data
+ * far from zero.  Both operands of a product must use the same origin. */
+int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d,
+                      const void* origin, void* xs, int64_t ld, cagp_stream_t stream);
 
 /* Mt = (K'(X1, X2) S)^T for a BlockDiagonalSparse S with non-zeros `s` (n) and k blocks.
  * Replaces LazyKernel._matmat applied to to_dense(BlockDiagonalSparse)

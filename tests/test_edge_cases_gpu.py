@@ -1,0 +1,123 @@
+"""Edge cases of the CUDA path: degenerate block layouts, far-apart points (underflow / clamp), tiny and
+huge lengthscales, single action, float32 predict, distribution surface (log_prob / sample)."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import cagpjax_b200 as cagp
+from cagpjax_b200 import _native as N, gpx
+from cagpjax_b200.distributions import GaussianDistribution
+from oracle import cagp_oracle as O
+from tests.util import make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("n,k", [(3, 5), (7, 1), (1, 1), (40, 40), (41, 40), (2049, 2)])
+def test_degenerate_block_layouts(n, k):
+    """More blocks than points (empty blocks), a single block, one row per block, a 2-block split of a
+    long vector (blocks longer than a CTA's rows -> split tiles / atomics)."""
+    d = 2
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64) * 3
+    s = torch.randn(n, generator=g, dtype=torch.float64)
+    ls = torch.tensor([0.9], dtype=torch.float64)
+    ref = O.projected_kernel_blocksparse("rbf", x.numpy(), x.numpy(), ls.numpy(), s.numpy(), k)
+    xs = N.scale_inputs("rbf", x.to(DEV), ls.to(DEV))
+    for Mt in (N.ks_blocksparse_fwd("rbf", xs, xs, d, s.to(DEV), k, ls.to(DEV)),
+               N.ks_blocksparse_fwd_sym("rbf", xs, d, s.to(DEV), k, ls.to(DEV))):
+        assert rel_err(Mt.T, ref) < 1e-12
+    model, data, p, x64, y64 = make_problem("rbf", n, d, k, seed=1)
+    val, grads = gpx.value_and_grad(lambda m, dd: m.elbo(m.init(dd)), model, data)
+    oval, ograds = O.elbo_and_grad_literal("rbf", x64, y64, p, k)
+    assert rel_err(val, oval) < 1e-10
+    gs, go = grads["BlockSparsePolicy.nz_values"].cpu(), ograds["actions"]
+    # (k = n: S is square and invertible, the ELBO is then independent of S up to the jitter, so the
+    #  gradient is a ~1e-6 remainder of O(100) cancelling terms: compare absolutely as well)
+    assert rel_err(gs, go) < 1e-8 or float((gs - go).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+def test_far_apart_points_underflow_to_zero(family):
+    """Distances far beyond the kernel's range (exp underflow in the reference): zeros / ~1e-301, never NaN
+    or inf; includes a point 1e9 lengthscales away (high-word overflow of the range reduction -> clamp)."""
+    x = torch.tensor([[0.0], [1.0], [50.0], [2000.0], [4e4], [1e9]], dtype=torch.float64)
+    s = torch.ones(6, dtype=torch.float64)
+    ls = torch.tensor([1.0], dtype=torch.float64)
+    ref = O.projected_kernel_blocksparse(family, x.numpy(), x.numpy(), ls.numpy(), s.numpy(), 6)
+    xs = N.scale_inputs(family, x.to(DEV), ls.to(DEV), x[0].to(DEV))
+    for Mt in (N.ks_blocksparse_fwd(family, xs, xs, 1, s.to(DEV), 6, ls.to(DEV)).cpu(),
+               N.ks_blocksparse_fwd_sym(family, xs, 1, s.to(DEV), 6, ls.to(DEV)).cpu()):
+        assert torch.isfinite(Mt).all()
+        assert np.max(np.abs(Mt.T.numpy() - ref)) < 1e-15  # absolute: the reference underflows to 0 as well
+
+
+def test_common_offset_is_removed_before_scaling():
+    """A data set far from zero (offset 1e7, spacing 0.25): the origin shift keeps differences exact."""
+    x = 1e7 + 0.25 * torch.arange(64, dtype=torch.float64)[:, None]
+    s = torch.ones(64, dtype=torch.float64)
+    ls = torch.tensor([0.7], dtype=torch.float64)
+    ref = O.projected_kernel_blocksparse("rbf", (x - 1e7).numpy(), (x - 1e7).numpy(), ls.numpy(), s.numpy(), 4)
+    xs = N.scale_inputs("rbf", x.to(DEV), ls.to(DEV), x[0].to(DEV))
+    Mt = N.ks_blocksparse_fwd_sym("rbf", xs, 1, s.to(DEV), 4, ls.to(DEV))
+    assert rel_err(Mt.T, ref) < 1e-13
+
+
+@pytest.mark.parametrize("ls", [1e-3, 1e3])
+def test_extreme_lengthscales(ls):
+    n, d, k = 500, 3, 5
+    model, data, p, x, y = make_problem("rbf", n, d, k)
+    model.posterior.prior.kernel.lengthscale = torch.tensor(ls, dtype=torch.float64, device=DEV)
+    p.lengthscale = torch.tensor(ls, dtype=torch.float64)
+    with torch.no_grad():
+        elbo = model.elbo(model.init(data))
+    ref = O.elbo_literal("rbf", x, y, p, k)
+    assert torch.isfinite(elbo) and rel_err(elbo, ref) < 1e-9
+
+
+def test_float32_predict_matches_float64_oracle():
+    model, data, p, x, y = make_problem("rbf", 2000, 3, 16, dtype=torch.float32, obs_stddev=0.5)
+    g = torch.Generator().manual_seed(5)
+    z = torch.rand(300, 3, generator=g, dtype=torch.float64) * 4
+    with torch.no_grad():
+        st = model.init(data)
+        q = model.predict(st, z.to(DEV, torch.float32))
+        assert q.mean.dtype == torch.float32 and q.variance.dtype == torch.float32
+    ost = O.cagp_init("rbf", x, y, p, 16)
+    om, ov = O.cagp_predict("rbf", ost, p, z)
+    assert rel_err(q.mean, om) < 1e-4 and rel_err(q.variance, ov) < 2e-3
+
+
+def test_gaussian_distribution_surface():
+    """distributions.py:48-106: mean / variance / stddev / covariance / log_prob / sample on the lazy
+    predictive covariance."""
+    model, data, p, x, y = make_problem("rbf", 200, 2, 8)
+    g = torch.Generator().manual_seed(6)
+    z = torch.rand(25, 2, generator=g, dtype=torch.float64) * 4
+    with torch.no_grad():
+        st = model.init(data)
+        q = model.predict(st, z.to(DEV))
+        assert isinstance(q, GaussianDistribution)
+        cov = q.covariance().to_dense()
+        assert torch.allclose(q.variance, torch.diagonal(cov), atol=1e-12)
+        assert torch.allclose(q.stddev**2, q.variance)
+        # operator products agree with the dense matrix
+        v = torch.randn(25, 3, generator=g, dtype=torch.float64).to(DEV)
+        assert torch.allclose(q.scale @ v, cov @ v, atol=1e-10)
+        ost = O.cagp_init("rbf", x, y, p, 8)
+        om, ov, ocov = O.cagp_predict("rbf", ost, p, z, full_cov=True)
+        value = (om + 0.1).to(DEV)
+        lp = q.log_prob(value)
+        Lc = torch.linalg.cholesky(ocov + 1e-6 * torch.eye(25, dtype=torch.float64))
+        diff = value.cpu() - om
+        ref = -0.5 * (25 * math.log(2 * math.pi) + 2 * torch.log(torch.diagonal(Lc)).sum()
+                      + diff @ torch.cholesky_solve(diff[:, None], Lc)[:, 0])
+        assert rel_err(lp, ref) < 1e-8
+        samples = q.sample(3, (4000,))
+        assert samples.shape == (4000, 25)
+        assert torch.allclose(samples.mean(0).cpu(), om, atol=0.05)
+        assert torch.allclose(samples.var(0).cpu(), ov, rtol=0.2, atol=1e-3)

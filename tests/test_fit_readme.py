@@ -56,7 +56,7 @@ def test_readme_example_training_trajectory(n_data=1000, n_actions=10, iters=60)
     assert rel < 1e-8, float(rel)
     # learned hyper-parameters agree
     got = [float(gpx.unwrap(t)) for t in (prior.kernel.lengthscale, prior.kernel.variance, likelihood.obs_stddev)]
-    want = [float(torch.nn.functional.softplus(r)) for r in raw]
+    want = [float(torch.nn.functional.softplus(r.detach())) for r in raw]
     for a, b in zip(got, want):
         assert abs(a - b) < 1e-7 * max(1.0, abs(b))
     # predictions with the trained model
