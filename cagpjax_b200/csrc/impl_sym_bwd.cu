@@ -7,7 +7,7 @@ namespace cagp_host {
 template <typename T>
 size_t sym_bwd_ws_bytes(int64_t n, int d, int k, bool ard, int a_begin, int a_end) {
     const int dp = cagp_padded_dim(d);
-    auto til = make_sym_tiling(n, k, a_begin, a_end, sym_rows(n, k, dp, ard));
+    auto til = make_sym_tiling(n, k, a_begin, a_end, sym_shape(n, k, dp, ard));
     const int64_t gx = sym_grid_x(til);
     const int gy = sym_choose_groups(til, gx > 0 ? gx : 1);
     return (size_t)(gx > 0 ? gx : 1) * gy * (ard ? dp : 1) * sizeof(T) + 256;
@@ -19,7 +19,8 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                  size_t ws_bytes, cudaStream_t stream) {
     const int dp = cagp_padded_dim(d);
     const bool ard = kd->n_lengthscale > 1;
-    const int rows = sym_rows(n, k, dp, ard);
+    const SymShape sh = sym_shape(n, k, dp, ard);
+    const int rows = sh.rows;
     return dispatch_dim(dp, [&](auto dc) {
         return dispatch_family(kd->family, [&](auto fc) {
             constexpr int D = decltype(dc)::value;
@@ -34,7 +35,7 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                     cagp::SymBwdArgs<T> a;
                     a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Gt = (const T*)Gt; a.ldg = ldg;
                     a.sbar = (T*)s_bar; a.ls_part = (T*)ws;
-                    a.til = make_sym_tiling(n, k, a_begin, a_end, R);
+                    a.til = make_sym_tiling(n, k, a_begin, a_end, sh);
                     const int64_t gx = sym_grid_x(a.til);
                     if (cudaMemsetAsync(s_bar, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset s_bar failed");
                     int64_t nparts = 0;
@@ -42,10 +43,16 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                         const int gy = sym_choose_groups(a.til, gx);
                         nparts = gx * gy;
                         if (ws_bytes < (size_t)nparts * NLS * sizeof(T)) return fail(CAGP_ERR_WORKSPACE, "ks sym bwd workspace too small");
-                        const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 2 + NT / 32)) * sizeof(T);
-                        auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC>;
-                        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                        const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + 2 * (NT / 32))) * sizeof(T);
+                        if (a.til.wpb < 8) {
+                            auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC, true>;
+                            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                            kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                        } else {
+                            auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC, false>;
+                            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                            kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                        }
                         if (int rc2 = check_launch("ks_sym_bwd_kernel")) return rc2;
                     }
                     cagp::bwd_finalize_kernel<T><<<1, 256, 0, stream>>>(nullptr, 0, 0, nullptr, a.ls_part, nparts, NLS,

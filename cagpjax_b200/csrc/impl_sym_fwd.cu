@@ -7,7 +7,8 @@ template <typename T>
 int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int d, const void* s, int k,
                  int a_begin, int a_end, void* Mt, int64_t ldm, cudaStream_t stream) {
     const int dp = cagp_padded_dim(d);
-    const int rows = sym_rows(n, k, dp, false);
+    const SymShape sh = sym_shape(n, k, dp, false);
+    const int rows = sh.rows;
     return dispatch_dim(dp, [&](auto dc) {
         return dispatch_family(kd->family, [&](auto fc) {
             constexpr int D = decltype(dc)::value;
@@ -18,7 +19,7 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 constexpr int JC = ColsPerStage<D>::value;
                 cagp::SymFwdArgs<T> a;
                 a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Mt = (T*)Mt; a.ldm = ldm;
-                a.til = make_sym_tiling(n, k, a_begin, a_end, R);
+                a.til = make_sym_tiling(n, k, a_begin, a_end, sh);
                 const int64_t gx = sym_grid_x(a.til);
                 if (gx < 1) return (int)CAGP_OK;
                 const int gy = sym_choose_groups(a.til, gx);
@@ -29,9 +30,15 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                     if (cudaMemsetAsync((T*)Mt + (size_t)(k - 1) * ldm, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
                 }
                 const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NT / 32)) * sizeof(T);
-                auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC>;
-                if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                if (a.til.wpb < 8) {
+                    auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC, true>;
+                    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                } else {
+                    auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC, false>;
+                    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                }
                 return check_launch("ks_sym_fwd_kernel");
             });
         });

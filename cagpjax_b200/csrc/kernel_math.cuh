@@ -112,6 +112,32 @@ struct Consts<float> {
     static constexpr float tiny = 1e-36f;
 };
 
+// q = sum_t (a_t - b_t)^2.  For D >= 6 two independent accumulation chains halve the dependent-FMA depth
+// (the Matern d = 8 kernels were latency-bound on the single chain).
+template <typename T, int D>
+__device__ __forceinline__ T sqdist(const T (&a)[D], const T (&b)[D]) {
+    if (D >= 6) {
+        T q0 = T(0), q1 = T(0);
+#pragma unroll
+        for (int t = 0; t < D; t += 2) {
+            const T d0 = a[t] - b[t];
+            q0 = fma(d0, d0, q0);
+            if (t + 1 < D) {
+                const T d1 = a[t + 1] - b[t + 1];
+                q1 = fma(d1, d1, q1);
+            }
+        }
+        return q0 + q1;
+    }
+    T q = T(0);
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        const T df = a[t] - b[t];
+        q = fma(df, df, q);
+    }
+    return q;
+}
+
 // K' from q.
 template <typename T, int FAM>
 __device__ __forceinline__ T kernel_value(T q, unsigned tab) {

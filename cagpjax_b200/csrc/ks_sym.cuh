@@ -35,35 +35,72 @@ __device__ __forceinline__ float shfl_next<float>(float v, int src_lane) {
     return __shfl_sync(0xffffffffu, v, src_lane);
 }
 
+// A CTA has NW = 8 warps.  Blocks with at most 32*R*wpb rows are served by `wpb` warps each, so one CTA
+// hosts G = NW / wpb consecutive row blocks ("sub-groups") that all face the SAME column block b: the
+// column stage in shared memory is shared, every warp keeps R rows of ONE block in registers.  Sub-group g
+// (block a0 + g) walks the offsets off0 - g, so that a + off = a0 + off0 = b for all of them.  Large
+// blocks use wpb = 8 (G = 1) and, if they exceed 256*R rows, several row sub-tiles with atomics.  The
+// last block (which absorbs n % k and may be up to twice as long) always gets its own CTAs.
 struct SymTiling {
     BlockLayout lay;
-    int tiles_main;     // row sub-tiles per main block
+    int wpb;            // warps per row block for the main blocks (1, 2, 4 or 8)
+    int tiles_main;     // row sub-tiles per main block (> 1 only when wpb == 8)
     int tiles_last;     // row sub-tiles of the last block
     int a_begin, a_end; // action blocks whose tiles this launch computes
-    int n_off;          // offsets 0 .. n_off-1
-    int offs_per_cta;
+    int n_off;          // tile offsets 0 .. n_off-1  (n_off = k/2 + 1)
+    int offs_per_cta;   // CTA-level offsets off0 per CTA (range [0, n_off + G - 1))
 
-    // decode blockIdx.x -> (a, row offset inside a, is block a split over several CTAs)
-    __device__ void decode(int bx, int rows_per_cta, int& a, int64_t& off_rows, bool& split) const {
-        const int n_main_in_range = (a_end == lay.k ? a_end - 1 : a_end) - a_begin;
-        const int64_t nmain = (int64_t)(n_main_in_range > 0 ? n_main_in_range : 0) * tiles_main;
-        if (bx < nmain) {
-            a = a_begin + bx / tiles_main;
-            off_rows = (int64_t)(bx % tiles_main) * rows_per_cta;
-            split = tiles_main > 1;
-        } else {
-            a = lay.k - 1;
-            off_rows = (int64_t)(bx - nmain) * rows_per_cta;
-            split = tiles_last > 1;
-        }
+    __host__ __device__ int groups() const { return 8 / wpb; }
+    __host__ __device__ int main_end() const { return a_end == lay.k ? a_end - 1 : a_end; }
+    __host__ __device__ int64_t main_ctas() const {
+        const int nb = main_end() - a_begin;
+        if (nb <= 0) return 0;
+        const int G = groups();
+        return (int64_t)((nb + G - 1) / G) * tiles_main;
     }
     // tile partner of a at offset off; returns false if (a, off) is not a tile of the schedule
-    __device__ bool partner(int a, int off, int& b) const {
+    __host__ __device__ bool partner(int a, int off, int& b) const {
+        if (off < 0 || off >= n_off) return false;
         if (off == 0) { b = a; return true; }
         if (2 * off == lay.k && a >= off) return false;
         b = a + off;
         if (b >= lay.k) b -= lay.k;
         return true;
+    }
+};
+
+// Per-CTA / per-warp placement shared by the forward and the backward kernel.
+struct SymPlace {
+    int a0;          // first row block of the CTA
+    int G;           // sub-groups (row blocks) in this CTA
+    int wpb;         // warps per sub-group
+    int64_t sub_off; // row offset of this CTA's sub-tile inside its block(s)
+    bool split;      // several CTAs share a row block -> column sums are accumulated atomically
+    int a_limit;     // row blocks >= a_limit do not exist for this CTA
+    int rows_stride; // row stride between a thread's R rows (= 32 * wpb)
+
+    // MULTI == false: the tiling has wpb == 8 (one row block per CTA); constants fold away
+    template <bool MULTI>
+    __device__ static SymPlace make(const SymTiling& t, int bx, int R) {
+        SymPlace p;
+        const int64_t nmain = t.main_ctas();
+        if (bx < nmain) {
+            p.wpb = MULTI ? t.wpb : 8;
+            p.G = MULTI ? t.groups() : 1;
+            p.a0 = t.a_begin + (int)(bx / t.tiles_main) * p.G;
+            p.sub_off = (int64_t)(bx % t.tiles_main) * (256 * R);
+            p.split = t.tiles_main > 1;
+            p.a_limit = t.main_end();
+        } else {
+            p.wpb = 8;
+            p.G = 1;
+            p.a0 = t.lay.k - 1;
+            p.sub_off = (int64_t)(bx - nmain) * (256 * R);
+            p.split = t.tiles_last > 1;
+            p.a_limit = t.lay.k;
+        }
+        p.rows_stride = 32 * p.wpb;
+        return p;
     }
 };
 
@@ -75,8 +112,9 @@ struct SymFwdArgs {
     SymTiling til;
 };
 
-template <typename T, int D, int FAM, int R, int NT, int JC>
+template <typename T, int D, int FAM, int R, int NT, int JC, bool MULTI>
 __global__ void __launch_bounds__(NT) ks_sym_fwd_kernel(const SymFwdArgs<T> p) {
+    static_assert(NT == 256, "the symmetric kernels assume 8 warps per CTA");
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
@@ -85,33 +123,44 @@ __global__ void __launch_bounds__(NT) ks_sym_fwd_kernel(const SymFwdArgs<T> p) {
     T* colacc = sc + JC;                  // [NW][JC]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, NT);
-    const BlockLayout& lay = p.til.lay;
+    const SymTiling& til = p.til;
+    const BlockLayout& lay = til.lay;
+    const SymPlace pl = SymPlace::make<MULTI>(til, blockIdx.x, R);
 
-    int a;
-    int64_t off_rows;
-    bool split;
-    p.til.decode(blockIdx.x, NT * R, a, off_rows, split);
-    const int64_t i0 = lay.start(a), len_a = lay.len(a);
+    const int kG = MULTI ? pl.G : 1, kWpb = MULTI ? pl.wpb : 8;
+    const int g = MULTI ? warp / kWpb : 0; // sub-group of this warp
+    const int a = pl.a0 + g;               // its row block
+    const bool a_ok = a < pl.a_limit;
+    const int64_t i0 = a_ok ? lay.start(a) : 0, len_a = a_ok ? lay.len(a) : 0;
     T ar[R][D], srow[R];
     int64_t irow[R];
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int64_t o = off_rows + r * NT + tid;
+        const int64_t o = pl.sub_off + (warp % kWpb) * 32 + lane + (int64_t)r * (32 * kWpb);
         valid[r] = o < len_a;
         irow[r] = i0 + (valid[r] ? o : (len_a > 0 ? len_a - 1 : 0));
-        if (len_a == 0) irow[r] = 0;
 #pragma unroll
         for (int t = 0; t < D; ++t) ar[r][t] = p.xs[t * p.ld + irow[r]];
         srow[r] = valid[r] ? p.s[irow[r]] : T(0);
     }
-    const int off_begin = blockIdx.y * p.til.offs_per_cta;
-    const int off_end = min(p.til.n_off, off_begin + p.til.offs_per_cta);
+    const int n_off0 = til.n_off + kG - 1;
+    const int off_begin = blockIdx.y * til.offs_per_cta;
+    const int off_end = min(n_off0, off_begin + til.offs_per_cta);
     const int next_lane = (lane + 1) & 31;
-    for (int off = off_begin; off < off_end; ++off) {
-        int b;
-        if (!p.til.partner(a, off, b)) continue;
-        const bool diag = (off == 0);
+    for (int off0 = off_begin; off0 < off_end; ++off0) {
+        // the column block is common to all sub-groups; a sub-group takes part if (a, off0 - g) is a tile
+        bool any = false;
+        for (int gg = 0; gg < kG; ++gg) {
+            int bb;
+            any = any || (pl.a0 + gg < pl.a_limit && til.partner(pl.a0 + gg, off0 - gg, bb));
+        }
+        if (!any) continue;
+        int b = pl.a0 + off0;
+        b = b % lay.k;
+        int bw;
+        const bool mine = a_ok && til.partner(a, off0 - g, bw);  // warp-uniform
+        const bool diag = (off0 - g == 0);
         const int64_t j0 = lay.start(b), len_b = lay.len(b);
         T racc[R];
 #pragma unroll
@@ -128,47 +177,50 @@ __global__ void __launch_bounds__(NT) ks_sym_fwd_kernel(const SymFwdArgs<T> p) {
                 sc[idx] = in ? p.s[j] : T(0);
             }
             __syncthreads();
-            for (int sub = 0; sub < clp; sub += 32) {
-                T cacc = T(0);
+            if (mine) {
+                for (int sub = 0; sub < clp; sub += 32) {
+                    T cacc = T(0);
 #pragma unroll 2
-                for (int t = 0; t < 32; ++t) {
-                    const int cidx = sub + ((lane + t) & 31);
-                    T xb[D];
+                    for (int t = 0; t < 32; ++t) {
+                        const int cidx = sub + ((lane + t) & 31);
+                        T xb[D];
 #pragma unroll
-                    for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
-                    const T w = sc[cidx];
-                    T cp = cacc;
+                        for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
+                        const T w = sc[cidx];
+                        T cp = cacc;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        T q = T(0);
-#pragma unroll
-                        for (int tt = 0; tt < D; ++tt) {
-                            const T df = ar[r][tt] - xb[tt];
-                            q = fma(df, df, q);
+                        for (int r = 0; r < R; ++r) {
+                            const T q = sqdist<T, D>(ar[r], xb);
+                            const T kv = kernel_value<T, FAM>(q, tab_s);
+                            racc[r] = fma(kv, w, racc[r]);
+                            cp = fma(kv, srow[r], cp);
                         }
-                        const T kv = kernel_value<T, FAM>(q, tab_s);
-                        racc[r] = fma(kv, w, racc[r]);
-                        cp = fma(kv, srow[r], cp);
+                        cacc = shfl_next<T>(cp, next_lane);
                     }
-                    cacc = shfl_next<T>(cp, next_lane);
+                    colacc[warp * JC + sub + lane] = cacc;
                 }
-                colacc[warp * JC + sub + lane] = cacc;
             }
-            if (!diag) {
-                __syncthreads();
+            __syncthreads();
+            // column sums: combine the warps of every sub-group that owns a symmetric tile
+            for (int gg = 0; gg < kG; ++gg) {
+                int bb;
+                const int ag = pl.a0 + gg;
+                if (!(ag < pl.a_limit && til.partner(ag, off0 - gg, bb)) || off0 - gg == 0) continue;
                 for (int idx = tid; idx < cl; idx += NT) {
                     T v = T(0);
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) v += colacc[w * JC + idx];
-                    T* dst = p.Mt + (int64_t)a * p.ldm + j0 + c0 + idx;
-                    if (split) atomicAdd(dst, v);
+                    for (int w = 0; w < kWpb; ++w) v += colacc[(gg * kWpb + w) * JC + idx];
+                    T* dst = p.Mt + (int64_t)ag * p.ldm + j0 + c0 + idx;
+                    if (pl.split) atomicAdd(dst, v);
                     else *dst = v;
                 }
             }
         }
+        if (mine) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (valid[r]) p.Mt[(int64_t)b * p.ldm + irow[r]] = racc[r];
+            for (int r = 0; r < R; ++r)
+                if (valid[r]) p.Mt[(int64_t)b * p.ldm + irow[r]] = racc[r];
+        }
+        (void)diag;
     }
 }
 
@@ -182,35 +234,37 @@ struct SymBwdArgs {
     SymTiling til;
 };
 
-template <typename T, int D, int FAM, bool ARD, int R, int NT, int JC>
+template <typename T, int D, int FAM, bool ARD, int R, int NT, int JC, bool MULTI>
 __global__ void __launch_bounds__(NT) ks_sym_bwd_kernel(const SymBwdArgs<T> p) {
+    static_assert(NT == 256, "the symmetric kernels assume 8 warps per CTA");
     constexpr int NW = NT / 32;
     constexpr int NLS = ARD ? D : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
     T* xc = tab + ExpTab<T>::kSmemElems;  // [D][JC]
     T* sc = xc + D * JC;                  // [JC]
-    T* gc = sc + JC;                      // [JC]
-    T* colacc = gc + JC;                  // [NW][JC]
+    T* gc = sc + JC;                      // [G][JC]  G[j, a_g] for the columns, one row per sub-group (G <= 8)
+    T* colacc = gc + NW * JC;             // [NW][JC]
     __shared__ T red[NW][NLS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, NT);
-    const BlockLayout& lay = p.til.lay;
+    const SymTiling& til = p.til;
+    const BlockLayout& lay = til.lay;
+    const SymPlace pl = SymPlace::make<MULTI>(til, blockIdx.x, R);
 
-    int a;
-    int64_t off_rows;
-    bool split;
-    p.til.decode(blockIdx.x, NT * R, a, off_rows, split);
-    const int64_t i0 = lay.start(a), len_a = lay.len(a);
+    const int kG = MULTI ? pl.G : 1, kWpb = MULTI ? pl.wpb : 8;
+    const int g = MULTI ? warp / kWpb : 0;
+    const int a = pl.a0 + g;
+    const bool a_ok = a < pl.a_limit;
+    const int64_t i0 = a_ok ? lay.start(a) : 0, len_a = a_ok ? lay.len(a) : 0;
     T ar[R][D], srow[R];
     int64_t irow[R];
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int64_t o = off_rows + r * NT + tid;
+        const int64_t o = pl.sub_off + (warp % kWpb) * 32 + lane + (int64_t)r * (32 * kWpb);
         valid[r] = o < len_a;
         irow[r] = i0 + (valid[r] ? o : (len_a > 0 ? len_a - 1 : 0));
-        if (len_a == 0) irow[r] = 0;
 #pragma unroll
         for (int t = 0; t < D; ++t) ar[r][t] = p.xs[t * p.ld + irow[r]];
         srow[r] = valid[r] ? p.s[irow[r]] : T(0);
@@ -224,19 +278,26 @@ __global__ void __launch_bounds__(NT) ks_sym_bwd_kernel(const SymBwdArgs<T> p) {
     }
 #pragma unroll
     for (int t = 0; t < NLS; ++t) ltot[t] = T(0);
-    const int off_begin = blockIdx.y * p.til.offs_per_cta;
-    const int off_end = min(p.til.n_off, off_begin + p.til.offs_per_cta);
+    const int n_off0 = til.n_off + kG - 1;
+    const int off_begin = blockIdx.y * til.offs_per_cta;
+    const int off_end = min(n_off0, off_begin + til.offs_per_cta);
     const int next_lane = (lane + 1) & 31;
-    const T* __restrict__ ga = p.Gt + (int64_t)a * p.ldg;  // G[j, a] for the columns
-    for (int off = off_begin; off < off_end; ++off) {
-        int b;
-        if (!p.til.partner(a, off, b)) continue;
-        const bool diag = (off == 0);
+    for (int off0 = off_begin; off0 < off_end; ++off0) {
+        bool any = false;
+        for (int gg = 0; gg < kG; ++gg) {
+            int bb;
+            any = any || (pl.a0 + gg < pl.a_limit && til.partner(pl.a0 + gg, off0 - gg, bb));
+        }
+        if (!any) continue;
+        const int b = (pl.a0 + off0) % lay.k;
+        int bw;
+        const bool mine = a_ok && til.partner(a, off0 - g, bw);
+        const bool diag = (off0 - g == 0);
         const int64_t j0 = lay.start(b), len_b = lay.len(b);
         T grow[R], l1[R][NLS];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            grow[r] = valid[r] ? p.Gt[(int64_t)b * p.ldg + irow[r]] : T(0);  // G[i, b]
+            grow[r] = (mine && valid[r]) ? p.Gt[(int64_t)b * p.ldg + irow[r]] : T(0);  // G[i, b]
 #pragma unroll
             for (int t = 0; t < NLS; ++t) l1[r][t] = T(0);
         }
@@ -250,62 +311,72 @@ __global__ void __launch_bounds__(NT) ks_sym_bwd_kernel(const SymBwdArgs<T> p) {
 #pragma unroll
                 for (int t = 0; t < D; ++t) xc[t * JC + idx] = in ? p.xs[t * p.ld + j] : T(0);
                 sc[idx] = in ? p.s[j] : T(0);
-                gc[idx] = in ? ga[j] : T(0);
+            }
+            for (int gg = 0; gg < kG; ++gg) {
+                const int ag = pl.a0 + gg;
+                const T* __restrict__ ga = p.Gt + (int64_t)(ag < pl.a_limit ? ag : 0) * p.ldg;  // G[j, a_g]
+                for (int idx = tid; idx < clp; idx += NT)
+                    gc[gg * JC + idx] = (idx < cl && ag < pl.a_limit) ? ga[j0 + c0 + idx] : T(0);
             }
             __syncthreads();
-            for (int sub = 0; sub < clp; sub += 32) {
-                T cacc = T(0);
+            if (mine) {
+                const T* __restrict__ gcg = gc + g * JC;
+                for (int sub = 0; sub < clp; sub += 32) {
+                    T cacc = T(0);
 #pragma unroll 2
-                for (int t = 0; t < 32; ++t) {
-                    const int cidx = sub + ((lane + t) & 31);
-                    T xb[D];
+                    for (int t = 0; t < 32; ++t) {
+                        const int cidx = sub + ((lane + t) & 31);
+                        T xb[D];
 #pragma unroll
-                    for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
-                    const T scol = sc[cidx];
-                    const T gcol = diag ? T(0) : gc[cidx];  // diagonal tile: ordered pairs, row part only
-                    const T gcol_row = gc[cidx];
-                    T cp = cacc;
+                        for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
+                        const T scol = sc[cidx];
+                        const T gcol_row = gcg[cidx];
+                        const T gcol = diag ? T(0) : gcol_row;  // diagonal tile: ordered pairs, row part only
+                        T cp = cacc;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        T q = T(0);
-                        T qt[D];
-#pragma unroll
-                        for (int tt = 0; tt < D; ++tt) {
-                            const T df = ar[r][tt] - xb[tt];
-                            if (ARD) {
-                                qt[tt] = df * df;
-                                q += qt[tt];
-                            } else {
-                                q = fma(df, df, q);
-                            }
-                        }
-                        T kv, h;
-                        kernel_value_grad<T, FAM>(q, tab_s, kv, h);
-                        sacc[r] = fma(kv, gcol_row, sacc[r]);
-                        cp = fma(kv, grow[r], cp);
-                        if (ARD) {
+                        for (int r = 0; r < R; ++r) {
+                            T q = T(0);
+                            T qt[D];
 #pragma unroll
                             for (int tt = 0; tt < D; ++tt) {
-                                const T hq = h * qt[tt];
-                                l1[r][tt] = fma(hq, scol, l1[r][tt]);
-                                l2[r][tt] = fma(hq, gcol, l2[r][tt]);
+                                const T df = ar[r][tt] - xb[tt];
+                                if (ARD) {
+                                    qt[tt] = df * df;
+                                    q += qt[tt];
+                                } else {
+                                    q = fma(df, df, q);
+                                }
                             }
-                        } else {
-                            const T hq = h * q;
-                            l1[r][0] = fma(hq, scol, l1[r][0]);
-                            l2[r][0] = fma(hq, gcol, l2[r][0]);
+                            T kv, h;
+                            kernel_value_grad<T, FAM>(q, tab_s, kv, h);
+                            sacc[r] = fma(kv, gcol_row, sacc[r]);
+                            cp = fma(kv, grow[r], cp);
+                            if (ARD) {
+#pragma unroll
+                                for (int tt = 0; tt < D; ++tt) {
+                                    const T hq = h * qt[tt];
+                                    l1[r][tt] = fma(hq, scol, l1[r][tt]);
+                                    l2[r][tt] = fma(hq, gcol, l2[r][tt]);
+                                }
+                            } else {
+                                const T hq = h * q;
+                                l1[r][0] = fma(hq, scol, l1[r][0]);
+                                l2[r][0] = fma(hq, gcol, l2[r][0]);
+                            }
                         }
+                        cacc = shfl_next<T>(cp, next_lane);
                     }
-                    cacc = shfl_next<T>(cp, next_lane);
+                    colacc[warp * JC + sub + lane] = cacc;
                 }
-                colacc[warp * JC + sub + lane] = cacc;
             }
-            if (!diag) {
-                __syncthreads();
+            __syncthreads();
+            for (int gg = 0; gg < kG; ++gg) {
+                int bb;
+                const int ag = pl.a0 + gg;
+                if (!(ag < pl.a_limit && til.partner(ag, off0 - gg, bb)) || off0 - gg == 0) continue;
                 for (int idx = tid; idx < cl; idx += NT) {
                     T v = T(0);
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) v += colacc[w * JC + idx];
+                    for (int w = 0; w < kWpb; ++w) v += colacc[(gg * kWpb + w) * JC + idx];
                     atomicAdd(p.sbar + j0 + c0 + idx, v);
                 }
             }
