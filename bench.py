@@ -262,7 +262,10 @@ def main():
     flops = pairs_per_launch * pair_flops(fam, dd, "bwd" in dom)
     achieved = flops / (kern_ms[dom] * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                "frac": achieved / FP64_PEAK_TFLOPS,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from an ncu
+                # capture of this command at N = 1 (profiles/r01_traffic_c3_sym.csv); algorithmic: G' = 8 n k bytes
+                "traffic": 8.84e9 if (args.config == "c3" and world == 1 and dom == "cagp_ks_blocksparse_bwd_sym") else None,
                 "note": "achieved = declared algorithmic flops (libm-exp cost model, SURVEY 8d: 3d+34 fwd / 3d+40 bwd per ordered pair) / CUDA-event kernel time; peak = measured DFMA stream (of measured; nominal 37.2). frac > 1 because the kernels spend fewer fp64 slots than the declared model (table-based exp2, symmetric tiles); fp64_pipe_frac = executed fp64 slots x 2 / time / peak is the pipe utilisation",
                 "pairs_per_sec": pairs_per_launch / (kern_ms[dom] * 1e-3),
                 "fp64_pipe_frac": (pairs_per_launch / (kern_ms[dom] * 1e-3)) * FP64_SLOTS_PER_PAIR.get(dom, 0.0) * 2.0 / 1e12 / FP64_PEAK_TFLOPS

@@ -60,7 +60,9 @@ class ElboFromStats(torch.autograd.Function):
         dj = dvec + jitter
         P = variance * A
         P.diagonal().add_(dj)
-        L = torch.linalg.cholesky(P)
+        # cholesky_ex without error checking: no host synchronisation (jnp.linalg.cholesky, which the
+        # reference uses, also returns NaNs instead of raising when P is not positive definite)
+        L = torch.linalg.cholesky_ex(P, check_errors=False).L
         Q = torch.cholesky_inverse(L)
         w = Q @ r
         Bv = (variance * variance) * B

@@ -23,4 +23,6 @@ def _lower_cholesky(A: LinearOperator) -> LinearOperator:
         return ScalarMul(torch.sqrt(c), A.shape, A.dtype, A.device)
     if isinstance(A, Identity):
         return A
-    return Triangular(torch.linalg.cholesky(A.to_dense()), lower=True)
+    # no error check => no host synchronisation; like jnp.linalg.cholesky (lower_cholesky.py:38 of the
+    # reference) a non-PD input yields NaNs rather than an exception
+    return Triangular(torch.linalg.cholesky_ex(A.to_dense(), check_errors=False).L, lower=True)
