@@ -34,6 +34,10 @@ CONFIGS = {
     "c2": dict(n=100_000, d=8, family="matern32", k=512, dtype="f64", desc="n=100k,d=8,Matern-3/2,k=512"),
     # profiling-size variant of c3: same block size (976 rows per action block), 1/16 of the pairs
     "c3s": dict(n=250_000, d=3, family="rbf", k=256, dtype="f64", desc="n=250k,d=3,RBF,BlockSparse k=256,float64 (c3 block size, ncu-sized)"),
+    # BASELINE config 5 shape (dense Gaussian action matrix, d = 16, k = 256) at a size one step of which
+    # takes seconds: n = 200k (the named n = 2M is 100x the pairs)
+    "c5s": dict(n=200_000, d=16, family="rbf", k=256, dtype="f64", dense=True, lengthscale=4.0,
+                desc="n=200k,d=16,RBF,dense Gaussian actions k=256,float64 (config-5 shape, reduced n)"),
     "c3": dict(n=1_000_000, d=3, family="rbf", k=1024, dtype="f64", desc="n=1M,d=3,RBF,BlockSparse k=1024,float64"),
 }
 
@@ -56,10 +60,15 @@ def synth(cfg, device, dtype):
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
     g = torch.Generator().manual_seed(11)
     x = torch.rand(n, d, generator=g, dtype=torch.float64) * 10.0
+    if cfg.get("dense"):
+        x = torch.randn(n, d, generator=torch.Generator().manual_seed(21), dtype=torch.float64)
     g = torch.Generator().manual_seed(12)
     y = torch.sin(x[:, 0]) * torch.cos(x[:, min(1, d - 1)]) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
     g = torch.Generator().manual_seed(13)
-    s = torch.randn(n, generator=g, dtype=torch.float64)
+    if cfg.get("dense"):
+        s = torch.randn(n, k, generator=torch.Generator().manual_seed(22), dtype=torch.float64) / n**0.5
+    else:
+        s = torch.randn(n, generator=g, dtype=torch.float64)
     return x.to(dtype), y.to(dtype), s.to(dtype)
 
 
@@ -70,11 +79,14 @@ def build_model(cfg, x, y, s, device, dtype, process_group=None):
 
     kern_cls = {"rbf": gpx.RBF, "matern12": gpx.Matern12, "matern32": gpx.Matern32, "matern52": gpx.Matern52}[cfg["family"]]
     t = lambda v: torch.tensor(v, dtype=dtype, device=device)
-    kernel = kern_cls(lengthscale=t(1.0), variance=t(1.0),
+    kernel = kern_cls(lengthscale=t(cfg.get("lengthscale", 1.0)), variance=t(1.0),
                       compute_engine=cagp.computations.LazyKernelComputation(process_group=process_group))
     prior = gpx.Prior(kernel=kernel, mean_function=gpx.Constant(t(0.0)))
     lik = gpx.Gaussian(cfg["n"], obs_stddev=t(0.1))
-    policy = cagp.BlockSparsePolicy(cfg["k"], _normalize_by_blocks(s, cfg["k"]).to(device))
+    if cfg.get("dense"):
+        policy = cagp.policies.DensePolicy(s.to(device))
+    else:
+        policy = cagp.BlockSparsePolicy(cfg["k"], _normalize_by_blocks(s, cfg["k"]).to(device))
     model = cagp.ComputationAwareGP(prior * lik, policy)
     data = gpx.Dataset(x.to(device), y.to(device).reshape(-1, 1))
     return model, data
@@ -257,9 +269,9 @@ def main():
     n, dd, k = cfg["n"], cfg["d"], cfg["k"]
     fam = cfg["family"]
     kern_ms = {nm: v[0] / v[1] for nm, v in per_kernel.items()}
-    dom = max((nm for nm in kern_ms if "ks_blocksparse" in nm), key=lambda nm: kern_ms[nm])
+    dom = max((nm for nm in kern_ms if "ks_" in nm), key=lambda nm: kern_ms[nm])
     pairs_per_launch = per_kernel[dom][2] / per_kernel[dom][1]
-    flops = pairs_per_launch * pair_flops(fam, dd, "bwd" in dom)
+    flops = pairs_per_launch * (pair_flops(fam, dd, "bwd" in dom) + (2.0 * k if "dense" in dom else 0.0))
     achieved = flops / (kern_ms[dom] * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS,

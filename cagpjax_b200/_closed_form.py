@@ -113,3 +113,27 @@ class ElboFromStats(torch.autograd.Function):
 
 def elbo_from_stats(A, B, c, r, q, yy, n, variance, sigma, jitter):
     return ElboFromStats.apply(A, B, c, r, q, yy, variance, sigma, n, 0.0 if jitter is None else float(jitter))
+
+
+def elbo_from_stats_dense(A, B, c, r, Qs, yy, n, variance, sigma, jitter):
+    """Same closed form for a DENSE action matrix: the projected noise covariance D = sigma^2 S^T S is a
+    dense k x k matrix (``Qs`` = S^T S), cf. models/cagp.py:185-199 with a dense ``obs_cov_proj``.  Plain
+    autograd on k-sized tensors (k is a few hundred on this path)."""
+    k = A.shape[0]
+    s2 = sigma**2
+    eye = torch.eye(k, dtype=A.dtype, device=A.device)
+    D = s2 * Qs
+    Dj = D + jitter * eye
+    P = variance * A + Dj
+    L = torch.linalg.cholesky_ex(P, check_errors=False).L
+    w = torch.cholesky_solve(r[:, None], L)[:, 0]
+    Bv = variance**2 * B
+    cv = variance * c
+    tr_QB = torch.diagonal(torch.cholesky_solve(Bv, L)).sum()
+    resid2 = yy - 2.0 * (w @ cv) + w @ (Bv @ w)
+    var_exp = -0.5 * n * (math.log(2.0 * math.pi) + torch.log(s2)) - 0.5 * (resid2 + n * variance - tr_QB) / s2
+    Lq = torch.linalg.cholesky_ex(Dj, check_errors=False).L
+    inner = torch.sum(torch.linalg.solve_triangular(L, Lq, upper=False) ** 2)
+    kl = 0.5 * (inner + 2.0 * torch.sum(torch.log(torch.diagonal(L))) - 2.0 * torch.sum(torch.log(torch.diagonal(Lq)))
+                + r @ w - k) - 0.5 * (w @ (D @ w))
+    return var_exp - kl

@@ -365,3 +365,61 @@ def kernel_matmat(family: str, X1, X2, lengthscale, V: torch.Tensor) -> torch.Te
         cols = [ks_matrix(family, X1, X2, lengthscale, V[:, c].contiguous(), 1)[0] for c in range(V.shape[1])]
         return torch.stack(cols, dim=1)
     return KernelMatmat.apply(X1, X2, lengthscale, V, family)
+
+
+# --------------------------------------------------------------------------------------------
+# Dense action matrices: the same row-sum-reducible statistics with a dense S (n, k)
+# --------------------------------------------------------------------------------------------
+class DenseProjectStats(torch.autograd.Function):
+    """(X, lengthscale, S, yt) -> (A', B', c') for a DENSE action matrix S (n, k):
+    M' = K'(X, X) S,  A' = S^T M',  B' = M'^T M',  c' = M'^T yt   (unit-variance kernel K').
+
+    Rows of X1 (hence of M') are sharded like in ``ProjectStats``: one dense kernel pass over the local
+    rows, one packed all-reduce of [A'|B'|c'].  Reverse mode: Mbar = S Abar + M'(Bbar + Bbar^T) + yt cbar^T on the
+    local rows, then S_bar = K'(X, X_local) Mbar (dense kernel, roles swapped) and the lengthscale pass;
+    one all-reduce of [S_bar | yt_bar | ls_bar]."""
+
+    @staticmethod
+    def forward(ctx, X, lengthscale, S, yt, family, shard, holder):
+        d = X.shape[1]
+        xs = N.scale_inputs(family, X, lengthscale, X[0])
+        whole = shard.begin == 0 and shard.end == shard.n
+        xs1 = xs if whole else xs[:, shard.begin:shard.end].contiguous()
+        Sc = S.contiguous()
+        M = N.ks_dense_fwd(family, xs1, xs, d, Sc, lengthscale)  # (m_local, k)
+        Sl, yl = Sc[shard.begin:shard.end], yt[shard.begin:shard.end]
+        A, B, c = Sl.T @ M, M.T @ M, M.T @ yl
+        if shard.sharded:
+            k = S.shape[1]
+            packed = torch.cat([A.reshape(-1), B.reshape(-1), c.reshape(-1)])
+            _all_reduce_sum(packed, shard.group)
+            kk = k * k
+            A, B, c = packed[:kk].view(k, k), packed[kk:2 * kk].view(k, k), packed[2 * kk:]
+        ctx.family, ctx.d, ctx.shard = family, d, shard
+        ctx.save_for_backward(xs, xs1, Sc, M, yt, lengthscale)
+        if holder is not None:
+            holder["M"] = M
+        return A, B, c
+
+    @staticmethod
+    def backward(ctx, Abar, Bbar, cbar):
+        xs, xs1, S, M, yt, lengthscale = ctx.saved_tensors
+        shard = ctx.shard
+        Sl, yl = S[shard.begin:shard.end], yt[shard.begin:shard.end]
+        Mbar = (Sl @ Abar + M @ (Bbar + Bbar.T) + torch.outer(yl, cbar)).contiguous()
+        S_bar = N.ks_dense_fwd(ctx.family, xs, xs1, ctx.d, Mbar, lengthscale)  # K'(X, X_local) Mbar, (n, k)
+        ls_bar = N.ks_dense_bwd_ls(ctx.family, xs1, xs, ctx.d, S, Mbar, lengthscale)
+        S_bar[shard.begin:shard.end] += M @ Abar.T
+        yt_bar = torch.zeros_like(yt)
+        yt_bar[shard.begin:shard.end] = M @ cbar
+        if shard.sharded:
+            n, k = S.shape
+            packed = torch.cat([S_bar.reshape(-1), yt_bar, ls_bar.reshape(-1)])
+            _all_reduce_sum(packed, shard.group)
+            S_bar, yt_bar, ls_bar = packed[:n * k].view(n, k), packed[n * k:n * k + n], packed[n * k + n:]
+        return None, ls_bar.reshape(lengthscale.shape), S_bar, yt_bar, None, None, None
+
+
+def dense_project_stats(family: str, X, lengthscale, S, yt, shard: Optional[RowShard] = None, holder=None):
+    shard = shard or RowShard.full(X.shape[0])
+    return DenseProjectStats.apply(X, lengthscale, S, yt, family, shard, holder)

@@ -58,9 +58,14 @@ class ProjectedDenseGram(LinearOperator):
         self.diag_terms = tuple(diag_terms)
 
     def to_dense(self) -> torch.Tensor:
+        from ..operators.lazy_kernel import _kernel_params
+
         S = self.actions.A
-        KS = self.lazy.dense_actions(self.actions)
-        out = S.T @ KS.to_dense()
+        proj = self.lazy._projections.get(("dense", id(S)))
+        if proj is not None:  # statistics of the (possibly row-sharded) fused pass registered by init
+            out = _kernel_params(self.lazy.kernel, self.lazy.x1)[1] * proj.A
+        else:
+            out = S.T @ self.lazy.dense_actions(self.actions).to_dense()
         for D in self.diag_terms:
             out = out + S.T @ (D @ S)
         return out

@@ -23,7 +23,7 @@ from ..interop import lazify
 from ..linalg import ProjectedKernelGram, congruence_transform
 from ..operators import BlockDiagonalSparse, LazyKernel, diag_like
 from ..operators.lazy_kernel import KernelActions, KernelDenseActions, _kernel_params
-from ..ops import PSD, LinearOperator, Triangular, diag
+from ..ops import PSD, Dense, LinearOperator, Triangular, diag
 from ..policies import AbstractBatchLinearSolverPolicy
 from ..solvers import AbstractLinearSolver, Cholesky
 
@@ -137,6 +137,8 @@ class ComputationAwareGP:
         projection = None
         if isinstance(actions, BlockDiagonalSparse) and isinstance(cov_xx, LazyKernel) and cov_xx.is_gram:
             projection = cov_xx.project(actions, residual)
+        elif isinstance(actions, Dense) and isinstance(cov_xx, LazyKernel) and cov_xx.is_gram:
+            projection = cov_xx.project_dense(actions, residual)
         obs_cov_proj = congruence_transform(actions, obs_cov)
         cov_prior_proj = congruence_transform(actions, cov_prior)
         cov_prior_proj_state = self.solver.init(cov_prior_proj)
@@ -189,10 +191,16 @@ class ComputationAwareGP:
         """Evidence lower bound: sum of variational expectations minus the prior KL (models/cagp.py:233-249)."""
         if state._projection is not None and isinstance(self.solver, Cholesky) \
                 and isinstance(state.cov_prior_proj_state, Triangular):
+            if isinstance(state.actions, Dense):
+                return self._elbo_fused_dense(state)
             return self._elbo_fused(state)
         return torch.sum(self.variational_expectation(state)) - self.prior_kl(state)
 
     # ------------------------------------------------------------------------------------------
+    def _elbo_fused_dense(self, state: ComputationAwareGPState) -> torch.Tensor:
+        """Dense action matrix: same k-sized statistics, dense projected noise covariance."""
+        return _elbo_fused_dense_impl(self, state)
+
     def _elbo_fused(self, state: ComputationAwareGPState) -> torch.Tensor:
         """ELBO from the k-sized statistics of the fused pass:
         sum_i var_i = n var - var^2 tr(P^-1 B'),  |y - mean|^2 = |r~|^2 - 2 var w.c' + var^2 w.B'w,
@@ -209,6 +217,19 @@ class ComputationAwareGP:
         yt = state._residual
         return elbo_from_stats(proj.A, proj.B, proj.c, state.residual_proj, q, yt @ yt, x.shape[0], var, sigma,
                                self.solver.jitter)
+
+
+def _elbo_fused_dense_impl(model, state):
+    from .._closed_form import elbo_from_stats_dense
+
+    proj = state._projection
+    x = torch.atleast_2d(state.train_data.X)
+    _, var = _kernel_params(model.posterior.prior.kernel, x)
+    sigma = unwrap(model.posterior.likelihood.obs_stddev).to(device=x.device, dtype=var.dtype)
+    S = state.actions.A
+    yt = state._residual
+    return elbo_from_stats_dense(proj.A, proj.B, proj.c, state.residual_proj, S.T @ S, yt @ yt, x.shape[0], var, sigma,
+                                 0.0 if model.solver.jitter is None else model.solver.jitter)
 
 
 def _kl_divergence_from_solvers(solver, mean_q, cov_q_state, mean_p, cov_p_state) -> torch.Tensor:

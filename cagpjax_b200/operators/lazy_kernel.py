@@ -68,6 +68,35 @@ class KernelProjection:
         return self._holder["Mt"]
 
 
+class DenseKernelProjection:
+    """Statistics A' = S^T K' S, B' = (K'S)^T (K'S), c' = (K'S)^T residual for a DENSE action matrix S,
+    computed by one dense kernel pass over this rank's rows (+ one all-reduce when sharded)."""
+
+    def __init__(self, lazy: "LazyKernel", actions, residual: torch.Tensor):
+        self.lazy, self.actions, self.residual = lazy, actions, residual
+        self._stats = None
+        self._holder = {}
+
+    def _compute(self):
+        if self._stats is None:
+            lz = self.lazy
+            ls, _ = _kernel_params(lz.kernel, lz.x1)
+            n = lz.shape[0]
+            shard = _fused.RowShard.full(n)
+            if lz.process_group is not None:
+                import torch.distributed as dist
+
+                shard = _fused.RowShard.for_rank(n, dist.get_rank(lz.process_group),
+                                                 dist.get_world_size(lz.process_group), lz.process_group)
+            self._stats = _fused.dense_project_stats(lz.kernel.name, lz.x1, ls, self.actions.A.to(lz.dtype),
+                                                     self.residual.contiguous(), shard, self._holder)
+        return self._stats
+
+    A = property(lambda self: self._compute()[0])
+    B = property(lambda self: self._compute()[1])
+    c = property(lambda self: self._compute()[2])
+
+
 class KernelActions(LinearOperator):
     """Lazy (m, k) operator K(x1, x2) @ S for block-sparse S (the reference's ``cov_zx @ actions``,
     models/cagp.py:160).  Backed by the k-major projection ``Mt`` computed by one kernel pass."""
@@ -230,6 +259,17 @@ class LazyKernel(LinearOperator):
         if isinstance(other, Dense):
             return self.dense_actions(other)
         return super().__matmul__(other)
+
+    def project_dense(self, actions, residual: torch.Tensor) -> DenseKernelProjection:
+        """Fused statistics of K'(X, X) S for a dense S (Gram operators only)."""
+        if not self.is_gram:
+            raise ValueError("project_dense() needs a Gram operator (x1 is x2)")
+        key = ("dense", id(actions.A))
+        proj = self._projections.get(key)
+        if proj is None or proj.residual is not residual:
+            proj = DenseKernelProjection(self, actions, residual)
+            self._projections[key] = proj
+        return proj
 
     def dense_actions(self, actions) -> KernelDenseActions:
         """K @ S for dense S, memoised per action tensor so that one kernel pass serves every consumer."""
