@@ -7,11 +7,13 @@
 // walks the n columns of K' in chunks of JC = 32:
 //   phase A: the 256 threads evaluate the 64 x 32 kernel tile once (8 values each, row coordinates in
 //            registers, column coordinates broadcast from shared memory) and park it in shared memory;
-//   phase B: register-tiled FMA GEMM tile (8 rows x 4 columns per thread): the K' values of a warp's 8
-//            rows are warp-broadcast LDS.128s, the V values are conflict-free LDS.128s.
+//   phase B: the 64 x 128 output tile accumulates K'tile (64 x 32) * Vtile (32 x 128).  fp64: on the
+//            tensor core, mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no f64 kind), each warp a
+//            32 x 32 sub-tile = 16 accumulator fragments, 8 conflict-free LDS.64 per 16 MMAs.  fp32: an
+//            FMA register tile (8 rows x 4 columns per thread).
 // p > 128 takes ceil(p / 128) passes (grid.z) that re-evaluate the kernel tile (45 of ~300 fp64 slots
-// per pair at d = 16).  fp64 tensor-core MMA (DMMA) runs on the same datapath as DFMA on B200
-// (profiles/r01_issue_model.txt), so the FMA formulation loses no peak throughput.
+// per pair at d = 16).  On B200 DMMA and DFMA share one datapath (37.1 vs 33.9 TFLOP/s measured,
+// profiles/r01_issue_model.txt): the MMA form wins by needing 8x fewer issue slots, not by a higher peak.
 #pragma once
 #include "ks_blocksparse.cuh"
 
@@ -21,6 +23,17 @@ constexpr int kDenseRows = 64;    // rows per CTA
 constexpr int kDenseCols = 128;   // output columns per CTA pass
 constexpr int kDenseJC = 32;      // kernel columns per stage
 constexpr int kDenseThreads = 256;
+// shared-memory row strides: == 4 (mod 16) doubles so that the 16 lanes of a half-warp loading an
+// mma.m8n8k4 fragment (4 k-values x 4 rows/cols) hit 16 different bank pairs
+constexpr int kDenseKsStride = kDenseRows + 4;   // 68
+constexpr int kDenseVsStride = kDenseCols + 4;   // 132
+
+// D (8x8) += A (8x4, row) * B (4x8, col) in fp64 on the tensor core (DMMA.8x8x4).  Fragments: lane l holds
+// A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
 template <typename T>
 struct DenseFwdArgs {
@@ -50,10 +63,15 @@ __global__ void __launch_bounds__(kDenseThreads, 2) ks_dense_fwd_kernel(const De
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
     T* xc = tab + ExpTab<T>::kSmemElems;  // [D][JC]
-    T* Ks = xc + D * JC;                  // [JC][TM]
-    T* Vs = Ks + JC * TM;                 // [JC][TP]
+    constexpr int KS = kDenseKsStride, VS = kDenseVsStride;
+    constexpr bool kMma = sizeof(T) == 8;  // fp64: tensor-core MMA for the GEMM phase; fp32: FMA register tile
+    T* Ks = xc + D * JC;                  // [JC][KS]
+    T* Vs = Ks + JC * KS;                 // [JC][VS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, kDenseThreads);
+    // MMA warp tile: 32 rows x 32 columns (2 x 4 warp grid): 4 x 4 m8n8 accumulator tiles per warp
+    const int wm = warp & 1, wn = warp >> 1;
+    const int grp = lane >> 2, tig = lane & 3;
 
     const int64_t row0 = (int64_t)blockIdx.x * TM;
     const int rowA = tid & (TM - 1);  // phase-A row of this thread
@@ -82,7 +100,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) ks_dense_fwd_kernel(const De
         for (int idx = tid; idx < JC * TP; idx += kDenseThreads) {
             const int jj = idx / TP, cc = idx % TP;
             const int gc = colbase + cc;
-            Vs[idx] = (jj < cl && gc < p.p) ? p.V[(c0 + jj) * p.ldv + gc] : T(0);
+            Vs[jj * VS + cc] = (jj < cl && gc < p.p) ? p.V[(c0 + jj) * p.ldv + gc] : T(0);
         }
         __syncthreads();
         // phase A: 64 x 32 kernel tile, 8 values per thread
@@ -95,34 +113,75 @@ __global__ void __launch_bounds__(kDenseThreads, 2) ks_dense_fwd_kernel(const De
                 const T df = ar[t] - xc[t * JC + jj];
                 q = fma(df, df, q);
             }
-            Ks[jj * TM + rowA] = kernel_value<T, FAM>(q, tab_s);
+            Ks[jj * KS + rowA] = (jj < cl) ? kernel_value<T, FAM>(q, tab_s) : T(0);
         }
         __syncthreads();
-        // phase B: acc[8][4] += K'[rows of this warp][jj] * V[jj][cols of this lane]
+        if constexpr (kMma) {
+            // phase B on the fp64 tensor core: acc[mt*4+nt] += K'[32 rows of the warp][4 k] * V[4 k][32 cols]
+#pragma unroll 2
+            for (int ks = 0; ks < JC / 4; ++ks) {
+                double af[4], bf[4];
+                const double* kp = reinterpret_cast<const double*>(Ks) + (ks * 4 + tig) * KS + wm * 32 + grp;
+                const double* vp = reinterpret_cast<const double*>(Vs) + (ks * 4 + tig) * VS + wn * 32 + grp;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    af[i] = kp[i * 8];
+                    bf[i] = vp[i * 8];
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+                        dmma_m8n8k4(*reinterpret_cast<double(*)[2]>(&acc[mt * 2 + nt / 2][(nt & 1) * 2]), af[mt], bf[nt]);
+            }
+        } else {
+            // phase B: acc[8][4] += K'[rows of this warp][jj] * V[jj][cols of this lane]
 #pragma unroll 4
-        for (int jj = 0; jj < JC; ++jj) {
-            T a[8], b[4];
-            load4<T>(Ks + jj * TM + warp * 8, *reinterpret_cast<T(*)[4]>(&a[0]));
-            load4<T>(Ks + jj * TM + warp * 8 + 4, *reinterpret_cast<T(*)[4]>(&a[4]));
-            load4<T>(Vs + jj * TP + lane * 4, b);
+            for (int jj = 0; jj < JC; ++jj) {
+                T a[8], b[4];
+                load4<T>(Ks + jj * KS + warp * 8, *reinterpret_cast<T(*)[4]>(&a[0]));
+                load4<T>(Ks + jj * KS + warp * 8 + 4, *reinterpret_cast<T(*)[4]>(&a[4]));
+                load4<T>(Vs + jj * VS + lane * 4, b);
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+                for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+            }
         }
     }
     const bool atomic = gridDim.y > 1;
+    if constexpr (kMma) {
+        // accumulator tile (mt, nt) lives in acc[mt*2 + nt/2][(nt&1)*2 + {0,1}]: row 8 mt + grp, cols 8 nt + 2 tig + {0,1}
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int64_t i = row0 + warp * 8 + r;
-        if (i >= p.m) continue;
+        for (int mt = 0; mt < 4; ++mt) {
+            const int64_t i = row0 + wm * 32 + mt * 8 + grp;
+            if (i >= p.m) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int gc = colbase + lane * 4 + c;
-            if (gc < p.p) {
-                T* dst = p.Y + i * p.ldy + gc;
-                if (atomic) atomicAdd(dst, acc[r][c]);
-                else *dst = acc[r][c];
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gc = colbase + wn * 32 + nt * 8 + 2 * tig + e;
+                    if (gc < p.p) {
+                        T* dst = p.Y + i * p.ldy + gc;
+                        const T v = acc[mt * 2 + nt / 2][(nt & 1) * 2 + e];
+                        if (atomic) atomicAdd(dst, v);
+                        else *dst = v;
+                    }
+                }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int64_t i = row0 + warp * 8 + r;
+            if (i >= p.m) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int gc = colbase + lane * 4 + c;
+                if (gc < p.p) {
+                    T* dst = p.Y + i * p.ldy + gc;
+                    if (atomic) atomicAdd(dst, acc[r][c]);
+                    else *dst = acc[r][c];
+                }
             }
         }
     }
@@ -142,15 +201,17 @@ struct DenseLsArgs {
 
 template <typename T, int D, int FAM, bool ARD>
 __global__ void __launch_bounds__(128, 3) ks_dense_bwd_ls_kernel(const DenseLsArgs<T> p) {
-    constexpr int TM = 64, TN = 64, PC = 32, NLS = ARD ? D : 1;
+    constexpr int TM = 64, TN = 64, PC = 32, NLS = ARD ? D : 1, ST = kDenseKsStride;
+    constexpr bool kMma = sizeof(T) == 8;  // fp64: score tile on the tensor core (DMMA); fp32: FMA register tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
-    T* Ys = tab + ExpTab<T>::kSmemElems;  // [PC][TM]
-    T* Vs = Ys + PC * TM;                 // [PC][TN]
+    T* Ys = tab + ExpTab<T>::kSmemElems;  // [PC][ST]
+    T* Vs = Ys + PC * ST;                 // [PC][ST]
     __shared__ T red[4][NLS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, 128);
-    const int rg = tid >> 4, cg = tid & 15;  // 8 row groups x 16 column groups
+    const int rg = tid >> 4, cg = tid & 15;  // FMA path: 8 row groups x 16 column groups
+    const int wm = warp & 1, wn = warp >> 1, grp = lane >> 2, tig = lane & 3;  // MMA path: 2 x 2 warps of 32 x 32
     const int64_t i0 = (int64_t)blockIdx.x * TM;
     T lacc[NLS];
 #pragma unroll
@@ -168,35 +229,57 @@ __global__ void __launch_bounds__(128, 3) ks_dense_bwd_ls_kernel(const DenseLsAr
             for (int idx = tid; idx < PC * TM; idx += 128) {
                 const int cc = idx / TM, ii = idx % TM;  // coalesced along the point axis (transposed operands)
                 const int64_t gi = i0 + ii;
-                Ys[idx] = (gi < p.m && c0 + cc < p.p) ? p.Ybt[(int64_t)(c0 + cc) * p.ldyb + gi] : T(0);
+                Ys[cc * ST + ii] = (gi < p.m && c0 + cc < p.p) ? p.Ybt[(int64_t)(c0 + cc) * p.ldyb + gi] : T(0);
                 const int64_t gj = j0 + ii;
-                Vs[idx] = (gj < j_end && c0 + cc < p.p) ? p.Vt[(int64_t)(c0 + cc) * p.ldv + gj] : T(0);
+                Vs[cc * ST + ii] = (gj < j_end && c0 + cc < p.p) ? p.Vt[(int64_t)(c0 + cc) * p.ldv + gj] : T(0);
             }
             __syncthreads();
+            if constexpr (kMma) {
+#pragma unroll 2
+                for (int ks = 0; ks < PC / 4; ++ks) {
+                    double af[4], bf[4];
+                    const double* yp = reinterpret_cast<const double*>(Ys) + (ks * 4 + tig) * ST + wm * 32 + grp;
+                    const double* vp = reinterpret_cast<const double*>(Vs) + (ks * 4 + tig) * ST + wn * 32 + grp;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        af[i] = yp[i * 8];
+                        bf[i] = vp[i * 8];
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt)
+                            dmma_m8n8k4(*reinterpret_cast<double(*)[2]>(&z[mt * 2 + nt / 2][(nt & 1) * 2]), af[mt], bf[nt]);
+                }
+            } else {
 #pragma unroll 4
-            for (int cc = 0; cc < PC; ++cc) {
-                T a[8], b[4];
-                load4<T>(Ys + cc * TM + rg * 8, *reinterpret_cast<T(*)[4]>(&a[0]));
-                load4<T>(Ys + cc * TM + rg * 8 + 4, *reinterpret_cast<T(*)[4]>(&a[4]));
-                load4<T>(Vs + cc * TN + cg * 4, b);
+                for (int cc = 0; cc < PC; ++cc) {
+                    T a[8], b[4];
+                    load4<T>(Ys + cc * ST + rg * 8, *reinterpret_cast<T(*)[4]>(&a[0]));
+                    load4<T>(Ys + cc * ST + rg * 8 + 4, *reinterpret_cast<T(*)[4]>(&a[4]));
+                    load4<T>(Vs + cc * ST + cg * 4, b);
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
+                    for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) z[r][c] = fma(a[r], b[c], z[r][c]);
+                        for (int c = 0; c < 4; ++c) z[r][c] = fma(a[r], b[c], z[r][c]);
+                }
             }
         }
-        // epilogue: weight the scores with H q
+        // epilogue: weight the scores with H q.  Pair of z[ri][ci]:
+        //   MMA: tile (mt, nt) element e -> row 32 wm + 8 mt + grp, column 32 wn + 8 nt + 2 tig + e
+        //   FMA: row 8 rg + ri, column 4 cg + ci
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int64_t gi = i0 + rg * 8 + r;
+        for (int ri = 0; ri < (kMma ? 4 : 8); ++ri) {
+            const int64_t gi = i0 + (kMma ? wm * 32 + ri * 8 + grp : rg * 8 + ri);
             if (gi >= p.m) continue;
             T xr[D];
 #pragma unroll
             for (int t = 0; t < D; ++t) xr[t] = p.xs1[t * p.ld1 + gi];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int64_t gj = j0 + cg * 4 + c;
+            for (int ci = 0; ci < (kMma ? 8 : 4); ++ci) {
+                const int64_t gj = j0 + (kMma ? wn * 32 + (ci >> 1) * 8 + 2 * tig + (ci & 1) : cg * 4 + ci);
                 if (gj >= j_end) continue;
+                const T zv = kMma ? z[ri * 2 + (ci >> 2)][ci & 3] : z[ri][ci];
                 T q = T(0), qt[D];
 #pragma unroll
                 for (int t = 0; t < D; ++t) {
@@ -206,7 +289,7 @@ __global__ void __launch_bounds__(128, 3) ks_dense_bwd_ls_kernel(const DenseLsAr
                 }
                 T kv, h;
                 kernel_value_grad<T, FAM>(q, tab_s, kv, h);
-                const T zh = z[r][c] * h;
+                const T zh = zv * h;
                 if (ARD) {
 #pragma unroll
                     for (int t = 0; t < D; ++t) lacc[t] = fma(zh, qt[t], lacc[t]);
