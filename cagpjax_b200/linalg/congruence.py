@@ -112,6 +112,10 @@ def congruence_transform(A, B):
         split = _split_kernel_sum(B)
         if split is not None:
             return ProjectedKernelGram(A, split[0], split[1])
+    if isinstance(A, Dense):
+        split = _split_kernel_sum(B)
+        if split is not None:
+            return ProjectedDenseGram(A, split[0], split[1])
     if torch.is_tensor(A) and A.dim() == 1:
         return A @ (B @ A)
     return A.T @ (B @ A)
