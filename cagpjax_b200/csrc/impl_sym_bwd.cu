@@ -7,7 +7,7 @@ namespace cagp_host {
 template <typename T>
 size_t sym_bwd_ws_bytes(int64_t n, int d, int k, bool ard, int a_begin, int a_end) {
     const int dp = cagp_padded_dim(d);
-    auto til = make_sym_tiling(n, k, a_begin, a_end, sym_shape(n, k, dp, ard));
+    auto til = make_sym_tiling(n, k, a_begin, a_end, sym_shape(n, k, dp, ard, true));
     const int64_t gx = sym_grid_x(til);
     const int gy = sym_choose_groups(til, gx > 0 ? gx : 1);
     return (size_t)(gx > 0 ? gx : 1) * gy * (ard ? dp : 1) * sizeof(T) + 256;
@@ -19,19 +19,19 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                  size_t ws_bytes, cudaStream_t stream) {
     const int dp = cagp_padded_dim(d);
     const bool ard = kd->n_lengthscale > 1;
-    const SymShape sh = sym_shape(n, k, dp, ard);
-    const int rows = sh.rows;
+    const SymShape sh = sym_shape(n, k, dp, ard, true);
     return dispatch_dim(dp, [&](auto dc) {
         return dispatch_family(kd->family, [&](auto fc) {
             constexpr int D = decltype(dc)::value;
             constexpr int FAM = decltype(fc)::value;
-            return dispatch_rows<D>(rows, [&](auto rc) {
+            return dispatch_rows<D>(sh.rows, [&](auto rc) {
                 constexpr int R = decltype(rc)::value;
-                constexpr int NT = kSymThreads;
                 constexpr int JC = ColsPerStage<D>::value;
-                auto launch = [&](auto ardc) {
+                auto launch = [&](auto ardc, auto sp) {
                     constexpr bool ARD = decltype(ardc)::value;
+                    constexpr bool SPREAD = decltype(sp)::value;
                     constexpr int NLS = ARD ? D : 1;
+                    constexpr int NC = SPREAD ? R : 1;
                     cagp::SymBwdArgs<T> a;
                     a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Gt = (const T*)Gt; a.ldg = ldg;
                     a.sbar = (T*)s_bar; a.ls_part = (T*)ws;
@@ -43,16 +43,10 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                         const int gy = sym_choose_groups(a.til, gx);
                         nparts = gx * gy;
                         if (ws_bytes < (size_t)nparts * NLS * sizeof(T)) return fail(CAGP_ERR_WORKSPACE, "ks sym bwd workspace too small");
-                        const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + 2 * (NT / 32))) * sizeof(T);
-                        if (a.til.wpb < 8) {
-                            auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC, true>;
-                            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                            kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
-                        } else {
-                            auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, NT, JC, false>;
-                            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                            kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
-                        }
+                        const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NC * 9)) * sizeof(T);
+                        auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, JC, SPREAD>;
+                        if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        kern<<<dim3((unsigned)gx, (unsigned)gy), a.til.nthreads, smem, stream>>>(a);
                         if (int rc2 = check_launch("ks_sym_bwd_kernel")) return rc2;
                     }
                     cagp::bwd_finalize_kernel<T><<<1, 256, 0, stream>>>(nullptr, 0, 0, nullptr, a.ls_part, nparts, NLS,
@@ -60,12 +54,24 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                                                                          (T)cagp::family_grad_const(kd->family), (T*)ls_bar);
                     return check_launch("bwd_finalize_kernel");
                 };
-                // with per-dimension accumulators only R <= MaxRows/2 is instantiated
+                // per-dimension accumulators: only R <= MaxRows/2 is instantiated; SPREAD needs R >= 2
+                constexpr int RARD = MaxRows<D>::value > 1 ? MaxRows<D>::value / 2 : 1;
                 if (ard) {
-                    if constexpr (R <= (MaxRows<D>::value > 1 ? MaxRows<D>::value / 2 : 1)) return launch(std::true_type{});
-                    else return fail(CAGP_ERR_UNSUPPORTED, "ARD backward with %d rows per thread not instantiated", R);
+                    if constexpr (R <= RARD) {
+                        if (sh.spread) {
+                            if constexpr (R >= 2) return launch(std::true_type{}, std::true_type{});
+                            else return fail(CAGP_ERR_UNSUPPORTED, "spread shape needs R >= 2");
+                        }
+                        return launch(std::true_type{}, std::false_type{});
+                    } else {
+                        return fail(CAGP_ERR_UNSUPPORTED, "ARD backward with %d rows per thread not instantiated", R);
+                    }
                 }
-                return launch(std::false_type{});
+                if (sh.spread) {
+                    if constexpr (R >= 2) return launch(std::false_type{}, std::true_type{});
+                    else return fail(CAGP_ERR_UNSUPPORTED, "spread shape needs R >= 2");
+                }
+                return launch(std::false_type{}, std::false_type{});
             });
         });
     });

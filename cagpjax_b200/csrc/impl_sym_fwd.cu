@@ -8,14 +8,12 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                  int a_begin, int a_end, void* Mt, int64_t ldm, cudaStream_t stream) {
     const int dp = cagp_padded_dim(d);
     const SymShape sh = sym_shape(n, k, dp, false);
-    const int rows = sh.rows;
     return dispatch_dim(dp, [&](auto dc) {
         return dispatch_family(kd->family, [&](auto fc) {
             constexpr int D = decltype(dc)::value;
             constexpr int FAM = decltype(fc)::value;
-            return dispatch_rows<D>(rows, [&](auto rc) {
+            return dispatch_rows<D>(sh.rows, [&](auto rc) {
                 constexpr int R = decltype(rc)::value;
-                constexpr int NT = kSymThreads;
                 constexpr int JC = ColsPerStage<D>::value;
                 cagp::SymFwdArgs<T> a;
                 a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Mt = (T*)Mt; a.ldm = ldm;
@@ -29,17 +27,20 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 } else if (a.til.tiles_last > 1) {
                     if (cudaMemsetAsync((T*)Mt + (size_t)(k - 1) * ldm, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
                 }
-                const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NT / 32)) * sizeof(T);
-                if (a.til.wpb < 8) {
-                    auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC, true>;
+                auto launch = [&](auto sp) {
+                    constexpr bool SPREAD = decltype(sp)::value;
+                    constexpr int NC = SPREAD ? R : 1;
+                    const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NC * 8)) * sizeof(T);
+                    auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, JC, SPREAD>;
                     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
-                } else {
-                    auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, NT, JC, false>;
-                    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);
+                    kern<<<dim3((unsigned)gx, (unsigned)gy), a.til.nthreads, smem, stream>>>(a);
+                    return check_launch("ks_sym_fwd_kernel");
+                };
+                if (sh.spread) {
+                    if constexpr (R >= 2) return launch(std::true_type{});
+                    else return fail(CAGP_ERR_UNSUPPORTED, "spread shape needs R >= 2");
                 }
-                return check_launch("ks_sym_fwd_kernel");
+                return launch(std::false_type{});
             });
         });
     });

@@ -7,35 +7,31 @@ namespace cagp_host {
 
 constexpr int kSymThreads = 256;
 
-// rows per thread R and warps per row block wpb for the main blocks: the smallest capacity
-// 32 * wpb * R that covers a block, preferring large R (column loads are amortised over R rows)
+// CTA shape for the symmetric kernels (see csrc/ks_sym.cuh): SPREAD for blocks of at most 256 rows when at
+// least two rows per thread fit in registers, SINGLE otherwise.
 struct SymShape {
-    int rows, wpb;
+    int rows, spread, nthreads;
 };
-inline SymShape sym_shape(int64_t n, int k, int dp, bool ard_bwd) {
+inline SymShape sym_shape(int64_t n, int k, int dp, bool ard_bwd, bool bwd = false) {
     int rmax = max_rows(dp);
     if (ard_bwd && rmax > 1) rmax /= 2;  // per-dimension accumulators double the register need
     const int64_t bs = n / k;
-    SymShape best{rmax, 8};
-    int64_t best_cap = -1;
-    for (int r = rmax; r >= 1; r /= 2) {
-        for (int w = 1; w <= 8; w *= 2) {
-            const int64_t cap = (int64_t)32 * w * r;
-            if (cap >= bs && (best_cap < 0 || cap < best_cap)) {
-                best_cap = cap;
-                best = SymShape{r, w};
-            }
-        }
+    if (bs >= 1 && bs <= kSymThreads && rmax >= 2 && k >= 2) {
+        // the spread backward kernel with 4 row blocks per thread needs 174 registers (1 CTA/SM): use 2
+        const int r = (bwd && rmax > 2) ? 2 : rmax;
+        return SymShape{r, 1, (int)((bs + 31) / 32 * 32)};
     }
-    return best;  // blocks larger than 256 * rmax: {rmax, 8} with several row sub-tiles
+    return SymShape{choose_rows(bs, kSymThreads, rmax), 0, kSymThreads};
 }
 
 inline cagp::SymTiling make_sym_tiling(int64_t n, int k, int a_begin, int a_end, SymShape sh) {
     cagp::SymTiling t;
     t.lay = cagp::BlockLayout{n, k, n / k};
-    t.wpb = sh.wpb;
-    const int64_t cap = (int64_t)kSymThreads * sh.rows;
-    t.tiles_main = sh.wpb == 8 ? (int)((t.lay.bs + cap - 1) / cap) : 1;
+    t.spread = sh.spread;
+    t.rows = sh.rows;
+    t.nthreads = sh.nthreads;
+    const int64_t cap = sh.spread ? (int64_t)sh.nthreads : (int64_t)sh.nthreads * sh.rows;
+    t.tiles_main = sh.spread ? 1 : (int)((t.lay.bs + cap - 1) / cap);
     if (t.tiles_main < 1) t.tiles_main = 1;
     t.tiles_last = (int)((t.lay.len(k - 1) + cap - 1) / cap);
     if (t.tiles_last < 1) t.tiles_last = 1;
@@ -51,7 +47,7 @@ inline int64_t sym_grid_x(const cagp::SymTiling& t) {
 }
 
 inline int sym_choose_groups(cagp::SymTiling& t, int64_t gx) {
-    const int n_off0 = t.n_off + t.groups() - 1;
+    const int n_off0 = t.n_off0();
     const int64_t target = (int64_t)num_sms() * 2 * 24;
     int64_t gy = (target + gx - 1) / gx;
     if (gy > n_off0) gy = n_off0;
