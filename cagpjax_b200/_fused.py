@@ -181,13 +181,14 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
     d = X.shape[1]
     xs = N.scale_inputs(family, X, lengthscale, X[0])
     whole = shard.begin == 0 and shard.end == shard.n
+    bbox = N.bounding_box(xs) if USE_SYMMETRIC and (whole or shard.block_aligned) else None
     if whole and USE_SYMMETRIC:
         # Gram case on one GPU: every kernel value is evaluated once per unordered block pair
         xs1 = xs
-        Mt = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale)
+        Mt = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, bbox=bbox)
     elif shard.block_aligned and USE_SYMMETRIC:
         xs1 = xs
-        Mfull = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end)
+        Mfull = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end, bbox=bbox)
         Mt = exchange_tiles_to_rows(Mfull, shard)
         del Mfull
     else:
@@ -197,12 +198,12 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
     yl = yt[shard.begin:shard.end].contiguous()
     A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)
     B = N.gram_mtm(Mt)
-    return A, B, c, Mt, xs, xs1
+    return A, B, c, Mt, xs, xs1, bbox
 
 
 def native_local_backward(family, X, lengthscale, s, yt, k, shard: RowShard, saved, Abar, Bbar, cbar):
     """Returns (s_bar_full_partial (n), yt_bar_local (m), ls_bar partial)."""
-    Mt, xs, xs1 = saved
+    Mt, xs, xs1, bbox = saved
     d = X.shape[1]
     sl = s[shard.begin:shard.end].contiguous()
     yl = yt[shard.begin:shard.end].contiguous()
@@ -210,10 +211,11 @@ def native_local_backward(family, X, lengthscale, s, yt, k, shard: RowShard, sav
     Gt = N.assemble_cotangent(Mt, shard.begin, shard.n, W, Abar.contiguous(), cbar.contiguous(), sl, yl)
     whole = shard.begin == 0 and shard.end == shard.n
     if whole and USE_SYMMETRIC:
-        s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale)
+        s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, bbox=bbox)
     elif shard.block_aligned and USE_SYMMETRIC:
         Gfull = gather_cotangent_for_tiles(Gt, shard)
-        s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gfull, lengthscale, shard.a_begin, shard.a_end)
+        s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gfull, lengthscale, shard.a_begin, shard.a_end,
+                                                 bbox=bbox)
         del Gfull
     else:
         s_bar, ls_bar = N.ks_blocksparse_bwd(family, xs1, xs, d, s, k, Gt, lengthscale)

@@ -30,6 +30,7 @@ class KernelDesc(Structure):
         ("n_lengthscale", c_int32),
         ("reserved", c_int32),
         ("lengthscale", c_void_p),
+        ("bbox", c_void_p),
     ]
 
 
@@ -37,6 +38,7 @@ _SIGNATURES = {
     "cagp_last_error_string": (c_char_p, []),
     "cagp_version": (c_int, []),
     "cagp_padded_dim": (c_int, [c_int32]),
+    "cagp_bounding_box": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
     "cagp_scale_inputs": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "cagp_ks_blocksparse_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                         c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
@@ -160,9 +162,21 @@ def _stream(t: torch.Tensor):
     return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def make_desc(family: str, lengthscale: torch.Tensor, dtype: torch.dtype) -> KernelDesc:
+def make_desc(family: str, lengthscale: torch.Tensor, dtype: torch.dtype, bbox: torch.Tensor = None) -> KernelDesc:
     ls = lengthscale.reshape(-1)
-    return KernelDesc(FAMILIES[family], dtype_code(dtype), ls.numel(), 0, ls.data_ptr())
+    return KernelDesc(FAMILIES[family], dtype_code(dtype), ls.numel(), 0, ls.data_ptr(),
+                      bbox.data_ptr() if bbox is not None else None)
+
+
+def bounding_box(xs: torch.Tensor) -> torch.Tensor:
+    """{min, max} per (padded) coordinate of scaled inputs xs (dpad, n) -> (2 * dpad,)."""
+    _require_cuda(xs)
+    dp, n = xs.shape
+    bbox = torch.empty(2 * dp, dtype=xs.dtype, device=xs.device)
+    with torch.cuda.device(xs.device), _timed("cagp_bounding_box", xs, 0):
+        _check(load().cagp_bounding_box(dtype_code(xs.dtype), _ptr(xs), n, n, dp, _ptr(bbox), _stream(xs)),
+               "cagp_bounding_box")
+    return bbox
 
 
 def padded_dim(d: int) -> int:
@@ -219,7 +233,7 @@ def ks_blocksparse_bwd(family, xs1, xs2, d, s, k, Gt, lengthscale):
     return s_bar, ls_bar
 
 
-def ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, a_begin=0, a_end=None, out=None) -> torch.Tensor:
+def ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, a_begin=0, a_end=None, out=None, bbox=None) -> torch.Tensor:
     """Symmetric Gram projection: Mt (k, n) entries of the tiles (a, a+off) for a in [a_begin, a_end)."""
     _require_cuda(xs, s)
     n = xs.shape[1]
@@ -227,20 +241,20 @@ def ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, a_begin=0, a_end=No
     full = a_begin == 0 and a_end == k
     Mt = out if out is not None else (torch.empty if full else torch.zeros)((k, n), dtype=xs.dtype, device=xs.device)
     ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
-    kd = make_desc(family, ls, xs.dtype)
+    kd = make_desc(family, ls, xs.dtype, bbox)
     with torch.cuda.device(xs.device), _timed("cagp_ks_blocksparse_fwd_sym", xs, n * n * (a_end - a_begin) // k):
         _check(load().cagp_ks_blocksparse_fwd_sym(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, _ptr(Mt), n,
                                                   _stream(xs)), "cagp_ks_blocksparse_fwd_sym")
     return Mt
 
 
-def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_end=None):
+def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_end=None, bbox=None):
     """(s_bar (n), ls_bar) contributions of the tiles of blocks [a_begin, a_end), full cotangent Gt (k, n)."""
     _require_cuda(xs, s, Gt)
     n = xs.shape[1]
     a_end = k if a_end is None else a_end
     ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
-    kd = make_desc(family, ls, xs.dtype)
+    kd = make_desc(family, ls, xs.dtype, bbox)
     lib = load()
     ws_bytes = lib.cagp_ks_bwd_sym_ws_bytes(byref(kd), n, d, k, a_begin, a_end)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs.device)

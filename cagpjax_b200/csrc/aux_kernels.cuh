@@ -28,6 +28,38 @@ __global__ void scale_inputs_kernel(const T* __restrict__ X, int64_t n, int d, c
     xs[(int64_t)t * ld + i] = v;
 }
 
+// bbox[t] = min_i xs[t][i], bbox[dp + t] = max_i xs[t][i]; one CTA per coordinate row (deterministic)
+template <typename T>
+__global__ void __launch_bounds__(1024) bounding_box_kernel(const T* __restrict__ xs, int64_t n, int64_t ld, int dp,
+                                                            T* __restrict__ bbox) {
+    __shared__ T smin[32], smax[32];
+    const int t = blockIdx.x;
+    const T* __restrict__ row = xs + (int64_t)t * ld;
+    T lo = row[0], hi = row[0];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const T v = row[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            lo = smin[w] < lo ? smin[w] : lo;
+            hi = smax[w] > hi ? smax[w] : hi;
+        }
+        // a NaN coordinate poisons the box (comparisons with NaN are false): mark it unusable
+        bbox[t] = lo;
+        bbox[dp + t] = hi;
+    }
+}
+
 // One CTA per action column b.  For every action block a intersecting the caller's rows
 // [row_offset, row_offset + m): A[a][b] = sum_i s_i Mt[b][i]; other rows of column b are zeroed.
 // c[b] = sum_i Mt[b][i] yt_i over all local rows.  s, yt are indexed by LOCAL row.

@@ -105,6 +105,17 @@ int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int3
     return check_launch("scale_inputs_kernel");
 }
 
+int cagp_bounding_box(int32_t dtype, const void* xs, int64_t n, int64_t ld, int32_t dpad, void* bbox, cagp_stream_t stream) {
+    if (!xs || !bbox || n < 1 || ld < n || dpad < 1) return fail(CAGP_ERR_INVALID, "bounding_box: bad argument");
+    if (dtype == CAGP_F64)
+        cagp::bounding_box_kernel<double><<<dpad, 1024, 0, (cudaStream_t)stream>>>((const double*)xs, n, ld, dpad, (double*)bbox);
+    else if (dtype == CAGP_F32)
+        cagp::bounding_box_kernel<float><<<dpad, 1024, 0, (cudaStream_t)stream>>>((const float*)xs, n, ld, dpad, (float*)bbox);
+    else
+        return fail(CAGP_ERR_INVALID, "unknown dtype");
+    return check_launch("bounding_box_kernel");
+}
+
 int cagp_ks_blocksparse_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2,
                             int64_t n, int64_t ld2, int32_t d, const void* s, int32_t k, void* Mt, int64_t ldm,
                             cagp_stream_t stream) {

@@ -36,6 +36,7 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                     a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Gt = (const T*)Gt; a.ldg = ldg;
                     a.sbar = (T*)s_bar; a.ls_part = (T*)ws;
                     a.til = make_sym_tiling(n, k, a_begin, a_end, sh);
+                    a.bbox = (const T*)kd->bbox;
                     const int64_t gx = sym_grid_x(a.til);
                     if (cudaMemsetAsync(s_bar, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset s_bar failed");
                     int64_t nparts = 0;

@@ -18,6 +18,7 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 cagp::SymFwdArgs<T> a;
                 a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Mt = (T*)Mt; a.ldm = ldm;
                 a.til = make_sym_tiling(n, k, a_begin, a_end, sh);
+                a.bbox = (const T*)kd->bbox;
                 const int64_t gx = sym_grid_x(a.til);
                 if (gx < 1) return (int)CAGP_OK;
                 const int gy = sym_choose_groups(a.til, gx);

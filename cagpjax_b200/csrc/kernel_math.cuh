@@ -65,6 +65,7 @@ struct ExpTab<float> {
 // |f| <= 2^-12 exactly, hence 2^(-u) = 2^(-(j >> 11)) * T[j & 2047] * 2^(-f): a table value, an
 // exponent adjustment and a cubic in f (Taylor remainder (2^-12 ln2)^4 / 24 = 3.4e-17).
 // fp64 pipe cost: 3 DADD + 3 DFMA + 1 DMUL (libm exp: 17 slots).
+template <bool SAFE = false>
 __device__ __forceinline__ double exp2neg(double u, unsigned tab_s) {
     constexpr double kMagic = 3298534883328.0;  // 1.5 * 2^41
     constexpr int kMagicHi = 0x42880000;        // its high word
@@ -81,15 +82,20 @@ __device__ __forceinline__ double exp2neg(double u, unsigned tab_s) {
     constexpr double c2 = 0.240226506959100712333551263163;
     constexpr double c3 = -0.0555041086648215799531422637686;
     const double p = fma(f, fma(f, fma(f, c3, c2), c1), 1.0);
-    // clamp the integer part at 1000 (also when u >= 2^21 spilled into the high word)
-    lo = (hi == kMagicHi) ? lo : 0xffffffffu;
-    lo = min(lo, 1000u << kExpTabBits);
+    // clamp the integer part at 1000 (also when u >= 2^21 spilled into the high word).  SAFE: the caller
+    // has proved u < 1000 for every pair of the launch (bounding box of the scaled inputs), no clamp.
+    if (!SAFE) {
+        lo = (hi == kMagicHi) ? lo : 0xffffffffu;
+        lo = min(lo, 1000u << kExpTabBits);
+    }
+    (void)hi;
     // table high words carry + (j << 9); subtracting lo << 9 = (n << 20) + (j << 9) leaves 2^-n * T[j]
     int thi;
     asm("mad.lo.s32 %0, %1, -512, %2;" : "=r"(thi) : "r"(lo), "r"(__double2hiint(tv)));
     return __hiloint2double(thi, __double2loint(tv)) * p;
 }
 
+template <bool SAFE = false>
 __device__ __forceinline__ float exp2neg(float u, unsigned) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-u));
@@ -139,13 +145,13 @@ __device__ __forceinline__ T sqdist(const T (&a)[D], const T (&b)[D]) {
 }
 
 // K' from q.
-template <typename T, int FAM>
+template <typename T, int FAM, bool SAFE = false>
 __device__ __forceinline__ T kernel_value(T q, unsigned tab) {
     if (FAM == RBF) {
-        return exp2neg(q, tab);
+        return exp2neg<SAFE>(q, tab);
     } else {
         const T tp = fast_sqrt(q);
-        const T e = exp2neg(tp, tab);
+        const T e = exp2neg<SAFE>(tp, tab);
         if (FAM == MATERN12) return e;
         const T r = tp * Consts<T>::ln2;
         if (FAM == MATERN32) return fma(r, e, e);
@@ -155,14 +161,14 @@ __device__ __forceinline__ T kernel_value(T q, unsigned tab) {
 }
 
 // K' and H (see header comment) from q.
-template <typename T, int FAM>
+template <typename T, int FAM, bool SAFE = false>
 __device__ __forceinline__ void kernel_value_grad(T q, unsigned tab, T& kv, T& h) {
     if (FAM == RBF) {
-        kv = exp2neg(q, tab);
+        kv = exp2neg<SAFE>(q, tab);
         h = kv;
     } else {
         const T tp = fast_sqrt(q);
-        const T e = exp2neg(tp, tab);
+        const T e = exp2neg<SAFE>(tp, tab);
         const T r = tp * Consts<T>::ln2;
         if (FAM == MATERN12) {
             kv = e;
@@ -175,6 +181,19 @@ __device__ __forceinline__ void kernel_value_grad(T q, unsigned tab, T& kv, T& h
             h = fma(r, e, e) * T(1.0 / 3.0);
         }
     }
+}
+
+// Launch-wide range proof: bbox = {min_0..min_{D-1}, max_0..max_{D-1}} of ALL scaled points of the launch (or
+// null).  q <= sum_t (max_t - min_t)^2; the exp2 argument is q (RBF) or sqrt(q) (Matern) and must stay < 1000.
+template <typename T, int D, int FAM>
+__device__ __forceinline__ bool launch_is_safe(const T* __restrict__ bbox) {
+    if (sizeof(T) == 4 || bbox == nullptr) return false;
+    T qm = T(0);
+    for (int t = 0; t < D; ++t) {
+        const T w = bbox[D + t] - bbox[t];
+        qm = fma(w, w, qm);
+    }
+    return FAM == RBF ? (qm < T(990)) : (qm < T(990) * T(990));  // false for NaN
 }
 
 // host+device: coordinate scale and gradient constant per family

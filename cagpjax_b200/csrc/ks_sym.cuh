@@ -20,6 +20,8 @@
 //   backward: s_bar_i += sum_j K'_ij Gt[a][j],  s_bar_j += sum_i K'_ij Gt[b][i]      (atomicAdd)
 //             ls_bar  += sum_ij H_ij q_ij (Gt[b][i] s_j + Gt[a][j] s_i)              (per-CTA partials)
 #pragma once
+#include <type_traits>
+
 #include "ks_blocksparse.cuh"
 
 namespace cagp {
@@ -78,6 +80,7 @@ struct SymFwdArgs {
     const T* xs; int64_t ld;
     const T* s;
     T* Mt; int64_t ldm;
+    const T* bbox;  // bounding box of the scaled inputs (2 * D values) or null
     SymTiling til;
 };
 
@@ -88,6 +91,7 @@ struct SymBwdArgs {
     const T* Gt; int64_t ldg;
     T* sbar;     // (n), zero-filled by the caller; accumulated with atomics
     T* ls_part;  // [gridDim.y * gridDim.x][NLS]
+    const T* bbox;  // bounding box of the scaled inputs (2 * D values) or null
     SymTiling til;
 };
 
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
     T* colacc = sc + JC;                  // [NC][NWMAX][JC]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, nthreads);
+    const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     const SymTiling& til = p.til;
     const BlockLayout& lay = til.lay;
     const SymRows<R, SPREAD> pl = SymRows<R, SPREAD>::make(til, blockIdx.x, tid, nthreads);
@@ -199,29 +204,38 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                 sc[idx] = in ? p.s[j] : T(0);
             }
             __syncthreads();
+            auto sweep = [&](auto safe_c) {
+                constexpr bool SAFE = decltype(safe_c)::value;
             for (int sub = 0; sub < clp; sub += 32) {
-                T cacc[NC];
+                    T cacc[NC];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) cacc[c] = T(0);
+                    for (int c = 0; c < NC; ++c) cacc[c] = T(0);
 #pragma unroll 2
-                for (int t = 0; t < 32; ++t) {
-                    const int cidx = sub + ((lane + t) & 31);
-                    T xb[D];
+                    for (int t = 0; t < 32; ++t) {
+                        const int cidx = sub + ((lane + t) & 31);
+                        T xb[D];
 #pragma unroll
-                    for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
-                    const T w = sc[cidx];
+                        for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
+                        const T w = sc[cidx];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const T q = sqdist<T, D>(ar[r], xb);
-                        const T kv = kernel_value<T, FAM>(q, tab_s);
-                        racc[r] = fma(kv, w, racc[r]);
-                        cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                        for (int r = 0; r < R; ++r) {
+                            const T q = sqdist<T, D>(ar[r], xb);
+                            const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
+                            racc[r] = fma(kv, w, racc[r]);
+                            cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
                     }
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
+                    for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
                 }
-#pragma unroll
-                for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
+            };
+            if constexpr (sizeof(T) == 8) {
+                if (safe) sweep(std::true_type{});
+                else sweep(std::false_type{});
+            } else {
+                sweep(std::false_type{});
             }
             __syncthreads();
             // column sums: Mt[a_c][j in b], for the row blocks that own a symmetric (off != 0) tile
@@ -258,6 +272,7 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
     __shared__ T red[NWMAX][NLS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, nthreads);
+    const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     const SymTiling& til = p.til;
     const BlockLayout& lay = til.lay;
     const SymRows<R, SPREAD> pl = SymRows<R, SPREAD>::make(til, blockIdx.x, tid, nthreads);
@@ -323,57 +338,66 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
                     gc[c * JC + idx] = (in && mine[c]) ? p.Gt[(int64_t)pl.a_of(c) * p.ldg + j] : T(0);  // handled below)
             }
             __syncthreads();
+            auto sweep = [&](auto safe_c) {
+                constexpr bool SAFE = decltype(safe_c)::value;
             for (int sub = 0; sub < clp; sub += 32) {
-                T cacc[NC];
+                    T cacc[NC];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) cacc[c] = T(0);
+                    for (int c = 0; c < NC; ++c) cacc[c] = T(0);
 #pragma unroll 2
-                for (int t = 0; t < 32; ++t) {
-                    const int cidx = sub + ((lane + t) & 31);
-                    T xb[D];
+                    for (int t = 0; t < 32; ++t) {
+                        const int cidx = sub + ((lane + t) & 31);
+                        T xb[D];
 #pragma unroll
-                    for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
-                    const T scol = sc[cidx];
+                        for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
+                        const T scol = sc[cidx];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int c = SPREAD ? r : 0;
-                        const T gcol_row = gc[c * JC + cidx];
-                        // diagonal tile (off == 0): ordered pairs, the row part only
-                        const T gcol = ((SPREAD ? off0 - c : off0) == 0) ? T(0) : gcol_row;
-                        T q = T(0);
-                        T qt[D];
-                        if (ARD) {
+                        for (int r = 0; r < R; ++r) {
+                            const int c = SPREAD ? r : 0;
+                            const T gcol_row = gc[c * JC + cidx];
+                            // diagonal tile (off == 0): ordered pairs, the row part only
+                            const T gcol = ((SPREAD ? off0 - c : off0) == 0) ? T(0) : gcol_row;
+                            T q = T(0);
+                            T qt[D];
+                            if (ARD) {
 #pragma unroll
-                            for (int tt = 0; tt < D; ++tt) {
-                                const T df = ar[r][tt] - xb[tt];
-                                qt[tt] = df * df;
-                                q += qt[tt];
+                                for (int tt = 0; tt < D; ++tt) {
+                                    const T df = ar[r][tt] - xb[tt];
+                                    qt[tt] = df * df;
+                                    q += qt[tt];
+                                }
+                            } else {
+                                q = sqdist<T, D>(ar[r], xb);
                             }
-                        } else {
-                            q = sqdist<T, D>(ar[r], xb);
-                        }
-                        T kv, h;
-                        kernel_value_grad<T, FAM>(q, tab_s, kv, h);
-                        sacc[r] = fma(kv, gcol_row, sacc[r]);
-                        cacc[c] = fma(kv, grow[r], cacc[c]);
-                        if (ARD) {
+                            T kv, h;
+                            kernel_value_grad<T, FAM, SAFE>(q, tab_s, kv, h);
+                            sacc[r] = fma(kv, gcol_row, sacc[r]);
+                            cacc[c] = fma(kv, grow[r], cacc[c]);
+                            if (ARD) {
 #pragma unroll
-                            for (int tt = 0; tt < D; ++tt) {
-                                const T hq = h * qt[tt];
-                                l1[r][tt] = fma(hq, scol, l1[r][tt]);
-                                l2[r][tt] = fma(hq, gcol, l2[r][tt]);
+                                for (int tt = 0; tt < D; ++tt) {
+                                    const T hq = h * qt[tt];
+                                    l1[r][tt] = fma(hq, scol, l1[r][tt]);
+                                    l2[r][tt] = fma(hq, gcol, l2[r][tt]);
+                                }
+                            } else {
+                                const T hq = h * q;
+                                l1[r][0] = fma(hq, scol, l1[r][0]);
+                                l2[r][0] = fma(hq, gcol, l2[r][0]);
                             }
-                        } else {
-                            const T hq = h * q;
-                            l1[r][0] = fma(hq, scol, l1[r][0]);
-                            l2[r][0] = fma(hq, gcol, l2[r][0]);
                         }
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
                     }
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
+                    for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
                 }
-#pragma unroll
-                for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
+            };
+            if constexpr (sizeof(T) == 8) {
+                if (safe) sweep(std::true_type{});
+                else sweep(std::false_type{});
+            } else {
+                sweep(std::false_type{});
             }
             __syncthreads();
 #pragma unroll

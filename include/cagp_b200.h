@@ -54,6 +54,10 @@ typedef struct cagp_kernel_desc {
   int32_t n_lengthscale;     /* 1 (isotropic) or d (ARD) */
   int32_t reserved;
   const void* lengthscale;   /* device pointer, n_lengthscale elements */
+  const void* bbox;          /* optional (may be NULL): device pointer to the bounding box of ALL scaled points
+                                of the call, {min_0..min_{D-1}, max_0..max_{D-1}} with D = cagp_padded_dim(d)
+                                (cagp_bounding_box).  Lets the symmetric kernels prove that no pair can reach
+                                the exp2 clamp and drop 3 integer instructions per kernel evaluation. */
 } cagp_kernel_desc;
 
 const char* cagp_last_error_string(void);
@@ -70,6 +74,10 @@ int cagp_padded_dim(int32_t d);
  * far from zero.  Both operands of a product must use the same origin. */
 int cagp_scale_inputs(const cagp_kernel_desc* kd, const void* X, int64_t n, int32_t d,
                       const void* origin, void* xs, int64_t ld, cagp_stream_t stream);
+
+/* Bounding box of scaled inputs xs (dpad, ld): bbox[t] = min_i xs[t][i], bbox[dpad + t] = max_i xs[t][i]. */
+int cagp_bounding_box(int32_t dtype, const void* xs, int64_t n, int64_t ld, int32_t dpad, void* bbox,
+                      cagp_stream_t stream);
 
 /* Mt = (K'(X1, X2) S)^T for a BlockDiagonalSparse S with non-zeros `s` (n) and k blocks.
  * Replaces LazyKernel._matmat applied to to_dense(BlockDiagonalSparse)

@@ -53,7 +53,7 @@ def test_native_argument_errors_are_reported_not_thrown():
     import ctypes
 
     lib = _native.load()
-    kd = _native.KernelDesc(7, 1, 1, 0, 0)
+    kd = _native.KernelDesc(7, 1, 1, 0, 0, None)
     rc = lib.cagp_scale_inputs(ctypes.byref(kd), None, 10, 2, None, None, 10, None)
     assert rc == 1 and b"family" in lib.cagp_last_error_string()
     assert lib.cagp_project_rows(1, None, 1, 1, 0, 1, 1, None, None, None, None, None) == 1
