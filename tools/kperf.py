@@ -40,6 +40,9 @@ t = timeit(lambda: N.assemble_cotangent(Mt, 0, n, W, W, c, sl, sl)); print(f"ass
 t = timeit(lambda: N.project_rows(Mt, 0, n, sl, sl)); print(f"project_rows: {t:.2f} ms  {Mt.numel()*Mt.element_size()/t/1e6:.0f} GB/s")
 t = timeit(lambda: N.project_rows_bwd(Mt, 0, n, W, c)); print(f"project_rows_bwd: {t:.2f} ms  {Mt.numel()*Mt.element_size()/t/1e6:.0f} GB/s")
 if m == n:
+    bb = N.bounding_box(xs2)
     t = timeit(lambda: N.ks_blocksparse_fwd_sym(fam, xs2, d, s, k, ls)); print(f"sym fwd: {t:.2f} ms  {n*n/t/1e6:.1f} G(ordered)pairs/s")
+    t = timeit(lambda: N.ks_blocksparse_fwd_sym(fam, xs2, d, s, k, ls, bbox=bb)); print(f"sym fwd (safe range): {t:.2f} ms  {n*n/t/1e6:.1f} G(ordered)pairs/s")
     Gf = torch.randn(k, n, dtype=dtype, device=dev)
     t = timeit(lambda: N.ks_blocksparse_bwd_sym(fam, xs2, d, s, k, Gf, ls)); print(f"sym bwd: {t:.2f} ms  {n*n/t/1e6:.1f} G(ordered)pairs/s")
+    t = timeit(lambda: N.ks_blocksparse_bwd_sym(fam, xs2, d, s, k, Gf, ls, bbox=bb)); print(f"sym bwd (safe range): {t:.2f} ms  {n*n/t/1e6:.1f} G(ordered)pairs/s")
