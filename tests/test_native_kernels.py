@@ -115,7 +115,11 @@ def test_predict_moments(dtype, m=700, k=12):
 
 SYM_SHAPES = [(9, 1, 4, False), (5, 2, 2, False), (6, 3, 3, True), (1037, 3, 10, False), (1500, 5, 7, True),
               (2000, 8, 64, False), (777, 16, 5, True), (3, 2, 5, False), (600, 20, 3, False), (4100, 3, 3, False),
-              (2500, 3, 2, True), (64, 2, 64, False), (1000, 1, 1, False)]
+              (2500, 3, 2, True), (64, 2, 64, False), (1000, 1, 1, False),
+              # SPREAD shape corner cases: even-k half offset, k not a multiple of the rows per thread, a last
+              # block longer than the CTA (atomics), blocks of exactly 256 rows, two blocks only
+              (300, 3, 2, False), (513, 2, 2, False), (1799, 3, 7, False), (2048, 4, 8, True), (1500, 8, 6, False),
+              (700, 3, 3, False)]
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
