@@ -48,7 +48,7 @@ inline int64_t sym_grid_x(const cagp::SymTiling& t) {
 
 inline int sym_choose_groups(cagp::SymTiling& t, int64_t gx) {
     const int n_off0 = t.n_off0();
-    const int64_t target = (int64_t)num_sms() * 2 * 24;
+    const int64_t target = (int64_t)num_sms() * 2 * 128;
     int64_t gy = (target + gx - 1) / gx;
     if (gy > n_off0) gy = n_off0;
     if (gy < 1) gy = 1;
