@@ -173,6 +173,44 @@ def _gather_cotangent_for_tiles(Gt_local: torch.Tensor, shard: RowShard, out: Op
 
 
 # --------------------------------------------------------------------------------------------
+# Peer-memory forward: compute + exchange in one kernel (NVLink / NVSwitch, torch symmetric memory)
+# --------------------------------------------------------------------------------------------
+USE_PEER_MEMORY = True   # falls back to the all_to_all exchange if symmetric memory is unavailable
+_peer_panels = {}        # (group id, k, ld, dtype, device) -> (symmetric tensor, handle)
+_peer_failed = False
+
+
+def _peer_panel(shard: RowShard, k: int, ld: int, dtype, device):
+    """Cached symmetric-memory scratch panel (k, ld) with its rendezvous handle (peer pointers, barrier)."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    key = (id(shard.group), k, ld, dtype, str(device))
+    ent = _peer_panels.get(key)
+    if ent is None:
+        t = symm_mem.empty((k, ld), dtype=dtype, device=device)
+        hdl = symm_mem.rendezvous(t, shard.group)
+        ent = (t, hdl)
+        _peer_panels[key] = ent
+    return ent
+
+
+def sym_forward_peer(family, xs, d, s, k, lengthscale, shard: RowShard, bbox) -> torch.Tensor:
+    """Symmetric Gram forward over the ranks of ``shard.group`` with the exchange fused into the kernel:
+    column sums that belong to another rank's rows are stored straight into that rank's panel through
+    peer-mapped memory.  Returns this rank's complete panel Mt (k, local rows)."""
+    world, me = shard.world, shard.rank
+    row_begin = [shard.peer_rows(r)[0] for r in range(world)] + [shard.n]
+    ld = max(row_begin[r + 1] - row_begin[r] for r in range(world))
+    panel, hdl = _peer_panel(shard, k, ld, xs.dtype, xs.device)
+    panel.zero_()         # column sums of row blocks split over several CTAs are accumulated atomically
+    hdl.barrier()         # every rank has zeroed its panel and finished reading it in the previous step
+    N.ks_blocksparse_fwd_sym_peer(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end,
+                                  [int(p) for p in hdl.buffer_ptrs], row_begin, me, ld, bbox=bbox)
+    hdl.barrier()         # all remote stores have landed
+    return panel[:, :shard.end - shard.begin].clone()
+
+
+# --------------------------------------------------------------------------------------------
 # Local compute (the part that runs native kernels).  Tests for the sharding logic replace this
 # with an oracle-backed callable on CPU (gloo); the product always uses the native one.
 # --------------------------------------------------------------------------------------------
@@ -187,10 +225,22 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
         xs1 = xs
         Mt = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, bbox=bbox)
     elif shard.block_aligned and USE_SYMMETRIC:
+        global _peer_failed
         xs1 = xs
-        Mfull = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end, bbox=bbox)
-        Mt = exchange_tiles_to_rows(Mfull, shard)
-        del Mfull
+        Mt = None
+        if USE_PEER_MEMORY and not _peer_failed and shard.world <= 16:
+            try:
+                with N._timed("host:sym_forward_peer", xs):
+                    Mt = sym_forward_peer(family, xs, d, s, k, lengthscale, shard, bbox)
+            except (RuntimeError, ImportError, AttributeError) as exc:  # no symmetric memory on this system
+                import warnings
+
+                _peer_failed = True
+                warnings.warn(f"peer-memory forward unavailable ({exc}); using the all_to_all exchange")
+        if Mt is None:
+            Mfull = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end, bbox=bbox)
+            Mt = exchange_tiles_to_rows(Mfull, shard)
+            del Mfull
     else:
         xs1 = xs if whole else xs[:, shard.begin:shard.end].contiguous()
         Mt = N.ks_blocksparse_fwd(family, xs1, xs, d, s, k, lengthscale)

@@ -44,6 +44,9 @@ _SIGNATURES = {
                                         c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "cagp_ks_blocksparse_fwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
                                             c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "cagp_ks_blocksparse_fwd_sym_peer": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
+                                                 c_int32, c_int32, POINTER(c_void_p), POINTER(c_int64), c_int32, c_int32,
+                                                 c_int64, c_void_p]),
     "cagp_ks_bwd_sym_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int32, c_int32, c_int32, c_int32]),
     "cagp_ks_blocksparse_bwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
                                             c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -75,7 +78,7 @@ _lib = None
 # optional CUDA-event timing of the pair kernels on the launching stream (bench.py sets PROFILE = []).
 LAUNCHES = 0
 PROFILE = None
-_KERNELS_PER_CALL = {"cagp_ks_dense_fwd": 1, "cagp_ks_dense_bwd_ls": 2, "cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
+_KERNELS_PER_CALL = {"cagp_ks_blocksparse_fwd_sym_peer": 1, "cagp_bounding_box": 1, "cagp_ks_dense_fwd": 1, "cagp_ks_dense_bwd_ls": 2, "cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
                      "cagp_project_rows": 1, "cagp_gram_mtm": 1, "cagp_assemble_cotangent": 1,
                      "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1}
 
@@ -246,6 +249,21 @@ def ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, a_begin=0, a_end=No
         _check(load().cagp_ks_blocksparse_fwd_sym(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, _ptr(Mt), n,
                                                   _stream(xs)), "cagp_ks_blocksparse_fwd_sym")
     return Mt
+
+
+def ks_blocksparse_fwd_sym_peer(family, xs, d, s, k, lengthscale, a_begin, a_end, panel_ptrs, row_begin, me, ldm,
+                                bbox=None) -> None:
+    """Peer-memory symmetric forward: row sums into this rank's panel, column sums straight into the owners' panels."""
+    _require_cuda(xs, s)
+    n = xs.shape[1]
+    world = len(panel_ptrs)
+    ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
+    kd = make_desc(family, ls, xs.dtype, bbox)
+    ptrs = (c_void_p * world)(*[c_void_p(int(p)) for p in panel_ptrs])
+    rb = (c_int64 * (world + 1))(*[int(v) for v in row_begin])
+    with torch.cuda.device(xs.device), _timed("cagp_ks_blocksparse_fwd_sym_peer", xs, n * n * (a_end - a_begin) // k):
+        _check(load().cagp_ks_blocksparse_fwd_sym_peer(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, ptrs, rb,
+                                                       world, me, ldm, _stream(xs)), "cagp_ks_blocksparse_fwd_sym_peer")
 
 
 def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_end=None, bbox=None):

@@ -132,8 +132,29 @@ int cagp_ks_blocksparse_fwd_sym(const cagp_kernel_desc* kd, const void* xs, int6
     if (int rc = check_desc(kd, d)) return rc;
     if (!xs || !s || !Mt) return fail(CAGP_ERR_INVALID, "ks sym fwd: null pointer");
     if (n < 1 || k < 1 || ld < n || ldm < n || a_begin < 0 || a_end > k || a_begin > a_end) return fail(CAGP_ERR_INVALID, "ks sym fwd: bad shape");
-    if (kd->dtype == CAGP_F64) return sym_fwd_impl<double>(kd, xs, n, ld, d, s, k, a_begin, a_end, Mt, ldm, (cudaStream_t)stream);
-    return sym_fwd_impl<float>(kd, xs, n, ld, d, s, k, a_begin, a_end, Mt, ldm, (cudaStream_t)stream);
+    void* panels[1] = {Mt};
+    const int64_t row_begin[2] = {0, n};
+    if (kd->dtype == CAGP_F64) return sym_fwd_impl<double>(kd, xs, n, ld, d, s, k, a_begin, a_end, panels, row_begin, 1, 0, ldm, (cudaStream_t)stream);
+    return sym_fwd_impl<float>(kd, xs, n, ld, d, s, k, a_begin, a_end, panels, row_begin, 1, 0, ldm, (cudaStream_t)stream);
+}
+
+int cagp_ks_blocksparse_fwd_sym_peer(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int32_t d,
+                                     const void* s, int32_t k, int32_t a_begin, int32_t a_end, void* const* panels,
+                                     const int64_t* row_begin, int32_t world, int32_t me, int64_t ldm,
+                                     cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs || !s || !panels || !row_begin) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: null pointer");
+    if (world < 1 || world > 16 || me < 0 || me >= world) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: bad world/rank");
+    if (n < 1 || k < 1 || ld < n || a_begin < 0 || a_end > k || a_begin > a_end) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: bad shape");
+    if (row_begin[0] != 0 || row_begin[world] != n) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: row_begin must span [0, n]");
+    const int64_t bs = n / k;
+    for (int r = 0; r < world; ++r) {
+        if (!panels[r]) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: null panel");
+        if (row_begin[r + 1] < row_begin[r] || row_begin[r + 1] - row_begin[r] > ldm) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: bad row partition");
+        if (r + 1 < world && bs > 0 && row_begin[r + 1] % bs != 0) return fail(CAGP_ERR_INVALID, "ks sym fwd peer: rows must be split on action-block boundaries");
+    }
+    if (kd->dtype == CAGP_F64) return sym_fwd_impl<double>(kd, xs, n, ld, d, s, k, a_begin, a_end, panels, row_begin, world, me, ldm, (cudaStream_t)stream);
+    return sym_fwd_impl<float>(kd, xs, n, ld, d, s, k, a_begin, a_end, panels, row_begin, world, me, ldm, (cudaStream_t)stream);
 }
 
 size_t cagp_ks_bwd_sym_ws_bytes(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t a_begin, int32_t a_end) {

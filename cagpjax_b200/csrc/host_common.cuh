@@ -78,7 +78,8 @@ int bwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
              void* ws, size_t ws_bytes, cudaStream_t stream);
 template <typename T>
 int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int d, const void* s, int k,
-                 int a_begin, int a_end, void* Mt, int64_t ldm, cudaStream_t stream);
+                 int a_begin, int a_end, void* const* panels, const int64_t* row_begin, int world, int me, int64_t ldm,
+                 cudaStream_t stream);
 template <typename T>
 size_t sym_bwd_ws_bytes(int64_t n, int d, int k, bool ard, int a_begin, int a_end);
 template <typename T>

@@ -5,7 +5,8 @@ namespace cagp_host {
 
 template <typename T>
 int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld, int d, const void* s, int k,
-                 int a_begin, int a_end, void* Mt, int64_t ldm, cudaStream_t stream) {
+                 int a_begin, int a_end, void* const* panels, const int64_t* row_begin, int world, int me, int64_t ldm,
+                 cudaStream_t stream) {
     const int dp = cagp_padded_dim(d);
     const SymShape sh = sym_shape(n, k, dp, false);
     return dispatch_dim(dp, [&](auto dc) {
@@ -16,17 +17,25 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 constexpr int R = decltype(rc)::value;
                 constexpr int JC = ColsPerStage<D>::value;
                 cagp::SymFwdArgs<T> a;
-                a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.Mt = (T*)Mt; a.ldm = ldm;
+                a.xs = (const T*)xs; a.ld = ld; a.s = (const T*)s; a.ldm = ldm;
+                a.world = world; a.me = me;
+                for (int r = 0; r < cagp::kMaxPeers; ++r) a.panel[r] = r < world ? (T*)panels[r] : nullptr;
+                for (int r = 0; r <= cagp::kMaxPeers; ++r) a.row_begin[r] = r <= world ? row_begin[r] : n;
+                void* Mt = panels[me];
+                const int64_t own_rows = row_begin[me + 1] - row_begin[me];
                 a.til = make_sym_tiling(n, k, a_begin, a_end, sh);
                 a.bbox = (const T*)kd->bbox;
                 const int64_t gx = sym_grid_x(a.til);
                 if (gx < 1) return (int)CAGP_OK;
                 const int gy = sym_choose_groups(a.til, gx);
                 // column sums of a block that is split over several CTAs are accumulated atomically
-                if (a.til.tiles_main > 1) {
-                    if (cudaMemsetAsync(Mt, 0, (size_t)k * ldm * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
-                } else if (a.til.tiles_last > 1) {
-                    if (cudaMemsetAsync((T*)Mt + (size_t)(k - 1) * ldm, 0, (size_t)n * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
+                // (single device only; in peer mode the caller zeroes the panels before the cross-rank barrier)
+                if (world == 1) {
+                    if (a.til.tiles_main > 1) {
+                        if (cudaMemsetAsync(Mt, 0, (size_t)k * ldm * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
+                    } else if (a.til.tiles_last > 1) {
+                        if (cudaMemsetAsync((T*)Mt + (size_t)(k - 1) * ldm, 0, (size_t)own_rows * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
+                    }
                 }
                 auto launch = [&](auto sp) {
                     constexpr bool SPREAD = decltype(sp)::value;
@@ -48,6 +57,6 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
 }
 
 template int sym_fwd_impl<CAGP_REAL>(const cagp_kernel_desc*, const void*, int64_t, int64_t, int, const void*, int, int,
-                                     int, void*, int64_t, cudaStream_t);
+                                     int, void* const*, const int64_t*, int, int, int64_t, cudaStream_t);
 
 }  // namespace cagp_host

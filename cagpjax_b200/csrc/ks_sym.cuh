@@ -75,11 +75,20 @@ struct SymTiling {
     }
 };
 
+constexpr int kMaxPeers = 16;
+
+// Output placement.  Single device: one panel Mt (k, ldm) holding all n columns (world = 1, row_begin =
+// {0, n}).  Peer mode (one process per GPU, NVLink peer memory): rank h owns the rows [row_begin[h],
+// row_begin[h+1]) - aligned to action blocks - and a panel (k, ldm) for them; a tile's row sums land in
+// the computing rank's own panel, its column sums are stored DIRECTLY into the panel of the rank that owns
+// the column block (remote st.global / red.global over NVLink), so the forward needs no collective.
 template <typename T>
 struct SymFwdArgs {
     const T* xs; int64_t ld;
     const T* s;
-    T* Mt; int64_t ldm;
+    T* panel[kMaxPeers]; int64_t ldm;
+    int64_t row_begin[kMaxPeers + 1];
+    int world, me;
     const T* bbox;  // bounding box of the scaled inputs (2 * D values) or null
     SymTiling til;
 };
@@ -189,6 +198,10 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
         if (!any) continue;
         const int b = (pl.a0 + off0) % lay.k;
         const int64_t j0 = lay.start(b), len_b = lay.len(b);
+        int owner = 0;  // rank that owns the rows of column block b
+        while (owner + 1 < p.world && j0 >= p.row_begin[owner + 1]) ++owner;
+        T* __restrict__ col_panel = p.panel[owner] - p.row_begin[owner];
+        T* __restrict__ row_panel = p.panel[p.me] - p.row_begin[p.me];
         T racc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) racc[r] = T(0);
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                 for (int idx = tid; idx < cl; idx += nthreads) {
                     T v = T(0);
                     for (int w = 0; w < nw; ++w) v += colacc[(c * NWMAX + w) * JC + idx];
-                    T* dst = p.Mt + (int64_t)ac * p.ldm + j0 + c0 + idx;
+                    T* dst = col_panel + (int64_t)ac * p.ldm + j0 + c0 + idx;
                     if (pl.split) atomicAdd(dst, v);
                     else *dst = v;
                 }
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (mine[SPREAD ? r : 0] && valid[r]) p.Mt[(int64_t)b * p.ldm + irow[r]] = racc[r];
+            if (mine[SPREAD ? r : 0] && valid[r]) row_panel[(int64_t)b * p.ldm + irow[r]] = racc[r];
     }
 }
 

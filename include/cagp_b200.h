@@ -112,6 +112,20 @@ int cagp_ks_blocksparse_fwd_sym(const cagp_kernel_desc* kd, const void* xs, int6
                                 int32_t d, const void* s, int32_t k, int32_t a_begin, int32_t a_end,
                                 void* Mt, int64_t ldm, cagp_stream_t stream);
 
+/* Peer-memory variant of the symmetric forward for one-process-per-GPU runs (NVLink / NVSwitch): the
+ * compute and the exchange are ONE kernel.  Rank r owns the rows [row_begin[r], row_begin[r+1]) (aligned
+ * to action blocks) and a panel (k, ldm) for them; `panels` lists all ranks' panels as pointers valid on
+ * THIS device (peer-mapped, e.g. symmetric memory).  The tiles of blocks [a_begin, a_end) are computed
+ * here; their row sums are stored into panels[me], their column sums directly into the panel of the rank
+ * that owns the column block (remote stores), which replaces the all-to-all that otherwise follows
+ * cagp_ks_blocksparse_fwd_sym.  Panels whose column sums are accumulated atomically (blocks split over
+ * several CTAs, i.e. row k-1) must be zeroed by their owners, and a cross-rank barrier must separate
+ * zeroing, this call and the first use of the panels.  `panels` / `row_begin` are HOST arrays. */
+int cagp_ks_blocksparse_fwd_sym_peer(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t ld,
+                                     int32_t d, const void* s, int32_t k, int32_t a_begin, int32_t a_end,
+                                     void* const* panels, const int64_t* row_begin, int32_t world,
+                                     int32_t me, int64_t ldm, cagp_stream_t stream);
+
 /* Reverse mode of the symmetric forward for the same tiles, given the FULL cotangent Gt (k, ldg >= n):
  * s_bar (n) and ls_bar (n_lengthscale) receive this call's tiles' contributions (s_bar is zeroed
  * first and accumulated with atomics: sums agree to rounding, not bitwise, between runs). */
