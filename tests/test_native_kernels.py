@@ -183,3 +183,28 @@ def test_ks_dense_fwd_bwd_match_oracle(dtype, family, n, m, d, p, ard):
     assert _rel(Vbar.cpu().numpy(), gV.numpy()) < tol
     lbar = N.ks_dense_bwd_ls(family, xs1, xs2, d, Vd, Ybd, LS)
     assert _rel(lbar.cpu().numpy(), gl.numpy()) < tol * 50
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("family,n,d,k", [("rbf", 1037, 3, 10), ("matern32", 2000, 8, 64), ("rbf", 4100, 3, 4), ("rbf", 700, 2, 7)])
+def test_ks_sym_fwd_peer_panels_emulated_on_one_gpu(world, family, n, d, k):
+    """The peer-memory forward (compute + exchange in one kernel): ranks emulated sequentially on one GPU,
+    every rank's panel being an ordinary buffer of this device.  After all ranks' tiles have run, panel h
+    holds the complete (K' S)^T restricted to the rows of rank h."""
+    from cagpjax_b200._fused import RowShard
+
+    x1, x2, s, ls = _data(n, n, d, k, 4, False)
+    ref = O.projected_kernel_blocksparse(family, x2.numpy(), x2.numpy(), ls.numpy(), s.numpy(), k)  # (n, k)
+    X2, S, LS = (t.to(DEV) for t in (x2, s, ls))
+    xs = N.scale_inputs(family, X2, LS, X2[0])
+    bb = N.bounding_box(xs)
+    shards = [RowShard.for_rank_blocks(n, k, r, world) for r in range(world)]
+    row_begin = [sh.begin for sh in shards] + [n]
+    ld = max(sh.end - sh.begin for sh in shards)
+    panels = [torch.zeros(k, ld, dtype=torch.float64, device=DEV) for _ in range(world)]
+    for me, sh in enumerate(shards):
+        N.ks_blocksparse_fwd_sym_peer(family, xs, d, S, k, LS, sh.a_begin, sh.a_end, [p.data_ptr() for p in panels],
+                                      row_begin, me, ld, bbox=bb)
+    for h, sh in enumerate(shards):
+        got = panels[h][:, :sh.end - sh.begin].T.cpu().numpy()
+        assert _rel(got, ref[sh.begin:sh.end]) < 2e-12
