@@ -145,7 +145,7 @@ int cagp_project_rows(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int
                       int64_t n_total, int32_t k, const void* s, const void* yt, void* A, void* c,
                       cagp_stream_t stream);
 
-/* B' = M'^T M' (k, k), full symmetric matrix, via cuBLAS syrk + mirror.  Replaces the lazy
+/* B' = M'^T M' (k, k), full symmetric matrix, via cuBLAS gemm (faster than syrk at these shapes) + mirror.  Replaces the lazy
  * inv_congruence_transform / cola.diag chain (solvers/cholesky.py:57-63, distributions.py:53-56)
  * whose trace only needs this k x k Gram matrix. */
 int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B,
