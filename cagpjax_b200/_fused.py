@@ -335,7 +335,7 @@ class KSMatrix(torch.autograd.Function):
         xs2 = N.scale_inputs(family, X2, lengthscale, X2[0])
         same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
         xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale, X2[0])
-        Mt = N.ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale)
+        Mt = N.ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale, N.union_bounding_box(xs1, xs2))
         ctx.family, ctx.k, ctx.d = family, k, d
         ctx.save_for_backward(xs1, xs2, s, lengthscale)
         return Mt

@@ -205,13 +205,13 @@ def scale_inputs(family: str, X: torch.Tensor, lengthscale: torch.Tensor, origin
     return xs
 
 
-def ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale) -> torch.Tensor:
-    """Mt (k, m) = (K'(X1, X2) S)^T."""
+def ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale, bbox=None) -> torch.Tensor:
+    """Mt (k, m) = (K'(X1, X2) S)^T.  ``bbox``: bounding box of BOTH scaled point sets (optional)."""
     _require_cuda(xs1, xs2, s)
     m, n = xs1.shape[1], xs2.shape[1]
     Mt = torch.empty((k, m), dtype=xs1.dtype, device=xs1.device)
     ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
-    kd = make_desc(family, ls, xs1.dtype)
+    kd = make_desc(family, ls, xs1.dtype, bbox)
     with torch.cuda.device(xs1.device), _timed("cagp_ks_blocksparse_fwd", xs1, m * n):
         _check(load().cagp_ks_blocksparse_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Mt), m,
                                               _stream(xs1)), "cagp_ks_blocksparse_fwd")
@@ -313,6 +313,16 @@ def ks_dense_bwd_ls(family, xs1, xs2, d, V, Ybar, lengthscale) -> torch.Tensor:
         _check(lib.cagp_ks_dense_bwd_ls(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(Vt), n, _ptr(Ybt), m, p,
                                         _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)), "cagp_ks_dense_bwd_ls")
     return ls_bar
+
+
+def union_bounding_box(xs1: torch.Tensor, xs2: torch.Tensor) -> torch.Tensor:
+    """Bounding box of two scaled point sets (same padded dimension)."""
+    b1 = bounding_box(xs1)
+    if xs1.data_ptr() == xs2.data_ptr() and xs1.shape == xs2.shape:
+        return b1
+    b2 = bounding_box(xs2)
+    dp = xs1.shape[0]
+    return torch.cat([torch.minimum(b1[:dp], b2[:dp]), torch.maximum(b1[dp:], b2[dp:])]).contiguous()
 
 
 def project_rows(Mt, row_offset, n_total, s_local, yt_local):

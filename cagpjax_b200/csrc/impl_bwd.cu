@@ -70,6 +70,7 @@ int bwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
                 a.ls_part = (T*)ws + (size_t)pl.n_ichunks * n;
                 a.tiles_main = pl.tiles_main;
                 a.ichunk = pl.ichunk;
+                a.bbox = nullptr;
                 const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
                 dim3 grid((unsigned)pl.gx, (unsigned)pl.n_ichunks);
                 if (ard) {

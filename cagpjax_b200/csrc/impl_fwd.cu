@@ -21,6 +21,7 @@ int fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
             a.s = (const T*)s;
             a.lay = cagp::BlockLayout{n, k, n / k};
             a.Mt = (T*)Mt; a.ldm = ldm;
+            a.bbox = (const T*)kd->bbox;
             const int64_t gx = (m + NT * R - 1) / (NT * R);
             const int64_t target = (int64_t)num_sms() * 4 * 32;
             int64_t gy = (target + gx - 1) / gx;

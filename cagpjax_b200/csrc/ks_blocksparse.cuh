@@ -13,6 +13,8 @@
 //             the lengthscale partial sum_i Gt[b][i] H_ij q_ij(t).  Column sums of the forward
 //             formulation become row sums here, so no cross-thread reduction is needed.
 #pragma once
+#include <type_traits>
+
 #include "kernel_math.cuh"
 
 namespace cagp {
@@ -71,6 +73,7 @@ struct FwdArgs {
     BlockLayout lay;
     T* Mt; int64_t ldm;
     int blocks_per_cta;
+    const T* bbox;  // bounding box of ALL scaled points of the call (2 * D values) or null
 };
 
 template <typename T, int D, int FAM, int R, int NT, int JC>
@@ -81,6 +84,7 @@ __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
     T* cols = tab + ExpTab<T>::kSmemElems;
     const int tid = threadIdx.x;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, NT);
+    const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
 
     const int64_t row0 = (int64_t)blockIdx.x * (NT * R);
     T a[R][D];
@@ -110,21 +114,30 @@ __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
                 cols[idx * E + D] = p.s[j];
             }
             __syncthreads();
+            auto sweep = [&](auto safe_c) {
+                constexpr bool SAFE = decltype(safe_c)::value;
 #pragma unroll 2
-            for (int j = 0; j < cl; ++j) {
-                T e[E];
-                load_entry_any<E>(cols + j * E, e);
+                for (int j = 0; j < cl; ++j) {
+                    T e[E];
+                    load_entry_any<E>(cols + j * E, e);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    T q = T(0);
+                    for (int r = 0; r < R; ++r) {
+                        T q = T(0);
 #pragma unroll
-                    for (int t = 0; t < D; ++t) {
-                        const T df = a[r][t] - e[t];
-                        q = fma(df, df, q);
+                        for (int t = 0; t < D; ++t) {
+                            const T df = a[r][t] - e[t];
+                            q = fma(df, df, q);
+                        }
+                        const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
+                        acc[r] = fma(kv, e[D], acc[r]);
                     }
-                    const T kv = kernel_value<T, FAM>(q, tab_s);
-                    acc[r] = fma(kv, e[D], acc[r]);
                 }
+            };
+            if constexpr (sizeof(T) == 8) {
+                if (safe) sweep(std::true_type{});
+                else sweep(std::false_type{});
+            } else {
+                sweep(std::false_type{});
             }
         }
 #pragma unroll
@@ -144,6 +157,7 @@ struct BwdArgs {
     T* ls_part;     // [gridDim.y * gridDim.x][NLS]
     int tiles_main; // tiles per main block
     int64_t ichunk; // streamed points per CTA
+    const T* bbox;  // bounding box of ALL scaled points of the call (2 * D values) or null
 };
 
 // ARD == false: one accumulator (isotropic lengthscale); ARD == true: D accumulators.

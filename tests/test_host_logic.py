@@ -172,6 +172,20 @@ def test_block_sparse_policy():
     assert torch.all(const.nz_values == const.nz_values[0])
 
 
+def test_orthogonalization_policy_passes_block_sparse_actions_through():
+    """Reference tests/test_policies.py:473-488."""
+    from cagpjax_b200.policies import DensePolicy, OrthogonalizationPolicy
+
+    base = BlockSparsePolicy.from_random(3, 12, 3)
+    pol = OrthogonalizationPolicy(base)
+    act = pol.to_actions(None)
+    assert isinstance(act, BlockDiagonalSparse) and pol.n_actions == 3
+    assert torch.equal(act.nz_values, base.nz_values)
+    dense = OrthogonalizationPolicy(DensePolicy(_rand(12, 3))).to_actions(None)
+    Q = dense.to_dense()
+    assert torch.allclose(Q.T @ Q, torch.eye(3, dtype=DT), atol=1e-12)
+
+
 # ---- LazyKernel host properties (reference tests/test_operators.py:236-260) -----------------------
 @pytest.mark.parametrize("batch_size,max_memory_mb", [(None, 0.0), (None, 32), (9, 32), (27, 0.0)])
 @pytest.mark.parametrize("checkpoint", [True, False])
