@@ -76,6 +76,8 @@ struct SymTiling {
 };
 
 constexpr int kMaxPeers = 16;
+// column tails of at most this many columns use the broadcast formulation instead of a 32-step ring
+constexpr int kSymTailBroadcast = 20;
 
 // Output placement.  Single device: one panel Mt (k, ldm) holding all n columns (world = 1, row_begin =
 // {0, n}).  Peer mode (one process per GPU, NVLink peer memory): rank h owns the rows [row_begin[h],
@@ -219,29 +221,52 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
             __syncthreads();
             auto sweep = [&](auto safe_c) {
                 constexpr bool SAFE = decltype(safe_c)::value;
-            for (int sub = 0; sub < clp; sub += 32) {
-                    T cacc[NC];
+                // one (thread, column) step: R kernel values feed the row sums and the column partials
+                auto pair_step = [&](int cidx, T (&cacc)[NC]) {
+                    T xb[D];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) cacc[c] = T(0);
+                    for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
+                    const T w = sc[cidx];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const T q = sqdist<T, D>(ar[r], xb);
+                        const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
+                        racc[r] = fma(kv, w, racc[r]);
+                        cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                    }
+                };
+                for (int sub = 0; sub < clp; sub += 32) {
+                    const int rem = cl - sub;
+                    if (rem > kSymTailBroadcast) {
+                        // ring: lane l visits column (l + t) mod 32 at step t, the column partial travels along
+                        T cacc[NC];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) cacc[c] = T(0);
 #pragma unroll 2
-                    for (int t = 0; t < 32; ++t) {
-                        const int cidx = sub + ((lane + t) & 31);
-                        T xb[D];
+                        for (int t = 0; t < 32; ++t) {
+                            pair_step(sub + ((lane + t) & 31), cacc);
 #pragma unroll
-                        for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
-                        const T w = sc[cidx];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const T q = sqdist<T, D>(ar[r], xb);
-                            const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
-                            racc[r] = fma(kv, w, racc[r]);
-                            cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                            for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
                         }
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
-                    }
+                        for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
+                    } else {
+                        // short tail of a block: all lanes take the same column, column sums by warp reduction
+                        // (a 32-step ring for a handful of columns would waste most of its slots)
+                        for (int jj = 0; jj < rem; ++jj) {
+                            T cp[NC];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
+                            for (int c = 0; c < NC; ++c) cp[c] = T(0);
+                            pair_step(sub + jj, cp);
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                T v = cp[c];
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                                if (lane == 0) colacc[(c * NWMAX + warp) * JC + sub + jj] = v;
+                            }
+                        }
+                    }
                 }
             };
             if constexpr (sizeof(T) == 8) {
@@ -353,57 +378,76 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
             __syncthreads();
             auto sweep = [&](auto safe_c) {
                 constexpr bool SAFE = decltype(safe_c)::value;
-            for (int sub = 0; sub < clp; sub += 32) {
-                    T cacc[NC];
+                auto pair_step = [&](int cidx, T (&cacc)[NC]) {
+                    T xb[D];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) cacc[c] = T(0);
+                    for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
+                    const T scol = sc[cidx];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int c = SPREAD ? r : 0;
+                        const T gcol_row = gc[c * JC + cidx];
+                        // diagonal tile (off == 0): ordered pairs, the row part only
+                        const T gcol = ((SPREAD ? off0 - c : off0) == 0) ? T(0) : gcol_row;
+                        T q = T(0);
+                        T qt[D];
+                        if (ARD) {
+#pragma unroll
+                            for (int tt = 0; tt < D; ++tt) {
+                                const T df = ar[r][tt] - xb[tt];
+                                qt[tt] = df * df;
+                                q += qt[tt];
+                            }
+                        } else {
+                            q = sqdist<T, D>(ar[r], xb);
+                        }
+                        T kv, h;
+                        kernel_value_grad<T, FAM, SAFE>(q, tab_s, kv, h);
+                        sacc[r] = fma(kv, gcol_row, sacc[r]);
+                        cacc[c] = fma(kv, grow[r], cacc[c]);
+                        if (ARD) {
+#pragma unroll
+                            for (int tt = 0; tt < D; ++tt) {
+                                const T hq = h * qt[tt];
+                                l1[r][tt] = fma(hq, scol, l1[r][tt]);
+                                l2[r][tt] = fma(hq, gcol, l2[r][tt]);
+                            }
+                        } else {
+                            const T hq = h * q;
+                            l1[r][0] = fma(hq, scol, l1[r][0]);
+                            l2[r][0] = fma(hq, gcol, l2[r][0]);
+                        }
+                    }
+                };
+                for (int sub = 0; sub < clp; sub += 32) {
+                    const int rem = cl - sub;
+                    if (rem > kSymTailBroadcast) {
+                        T cacc[NC];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) cacc[c] = T(0);
 #pragma unroll 2
-                    for (int t = 0; t < 32; ++t) {
-                        const int cidx = sub + ((lane + t) & 31);
-                        T xb[D];
+                        for (int t = 0; t < 32; ++t) {
+                            pair_step(sub + ((lane + t) & 31), cacc);
 #pragma unroll
-                        for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
-                        const T scol = sc[cidx];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int c = SPREAD ? r : 0;
-                            const T gcol_row = gc[c * JC + cidx];
-                            // diagonal tile (off == 0): ordered pairs, the row part only
-                            const T gcol = ((SPREAD ? off0 - c : off0) == 0) ? T(0) : gcol_row;
-                            T q = T(0);
-                            T qt[D];
-                            if (ARD) {
-#pragma unroll
-                                for (int tt = 0; tt < D; ++tt) {
-                                    const T df = ar[r][tt] - xb[tt];
-                                    qt[tt] = df * df;
-                                    q += qt[tt];
-                                }
-                            } else {
-                                q = sqdist<T, D>(ar[r], xb);
-                            }
-                            T kv, h;
-                            kernel_value_grad<T, FAM, SAFE>(q, tab_s, kv, h);
-                            sacc[r] = fma(kv, gcol_row, sacc[r]);
-                            cacc[c] = fma(kv, grow[r], cacc[c]);
-                            if (ARD) {
-#pragma unroll
-                                for (int tt = 0; tt < D; ++tt) {
-                                    const T hq = h * qt[tt];
-                                    l1[r][tt] = fma(hq, scol, l1[r][tt]);
-                                    l2[r][tt] = fma(hq, gcol, l2[r][tt]);
-                                }
-                            } else {
-                                const T hq = h * q;
-                                l1[r][0] = fma(hq, scol, l1[r][0]);
-                                l2[r][0] = fma(hq, gcol, l2[r][0]);
-                            }
+                            for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
                         }
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) cacc[c] = shfl_next<T>(cacc[c], next_lane);
-                    }
+                        for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
+                    } else {
+                        for (int jj = 0; jj < rem; ++jj) {
+                            T cp[NC];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) colacc[(c * NWMAX + warp) * JC + sub + lane] = cacc[c];
+                            for (int c = 0; c < NC; ++c) cp[c] = T(0);
+                            pair_step(sub + jj, cp);
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                T v = cp[c];
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                                if (lane == 0) colacc[(c * NWMAX + warp) * JC + sub + jj] = v;
+                            }
+                        }
+                    }
                 }
             };
             if constexpr (sizeof(T) == 8) {
