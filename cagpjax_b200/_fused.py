@@ -404,6 +404,38 @@ class KernelMatmat(torch.autograd.Function):
         return None, None, ls_bar, V_bar, None
 
 
+class CrossCovariance(torch.autograd.Function):
+    """C (m, n) = K'(X1, X2) materialised; differentiable w.r.t. lengthscale and X2 (the trainable pseudo-inputs of
+    PseudoInputPolicy, policies/pseudoinput.py:68-74), not X1 (the training inputs are non-trainable there)."""
+
+    @staticmethod
+    def forward(ctx, X1, X2, lengthscale, family):
+        d = X2.shape[1]
+        origin = X1[0].detach()
+        xs1 = N.scale_inputs(family, X1, lengthscale, origin)
+        xs2 = N.scale_inputs(family, X2, lengthscale, origin)
+        C = N.cross_cov_fwd(family, xs1, xs2, d, lengthscale)
+        ctx.family, ctx.d = family, d
+        ctx.save_for_backward(xs1, xs2, lengthscale)
+        return C
+
+    @staticmethod
+    def backward(ctx, Cbar):
+        xs1, xs2, lengthscale = ctx.saved_tensors
+        x2s_bar, ls_bar = N.cross_cov_bwd(ctx.family, xs1, xs2, ctx.d, Cbar, lengthscale)
+        X2_bar = None
+        if ctx.needs_input_grad[1]:
+            scale = N.family_scale(ctx.family) / lengthscale.reshape(-1).to(x2s_bar.dtype)  # (1,) or (d,)
+            X2_bar = x2s_bar[:ctx.d].T * scale
+        ls_out = ls_bar.reshape(lengthscale.shape) if ctx.needs_input_grad[2] else None
+        return None, X2_bar, ls_out, None
+
+
+def cross_covariance(family: str, X1, X2, lengthscale) -> torch.Tensor:
+    """Materialised unit-variance K'(X1, X2) (m, n) on the device."""
+    return CrossCovariance.apply(X1.contiguous(), X2.contiguous(), lengthscale, family)
+
+
 # Below this many columns a dense operand is cheaper as p one-block block-sparse passes (the pair
 # kernels run at ~950 Gpairs/s; the GEMM-shaped dense kernel shares one kernel tile across up to 128
 # output columns and only pays off when there are enough of them).

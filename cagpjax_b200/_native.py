@@ -16,6 +16,15 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libcagp_b200.so")
 
 FAMILIES = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+
+
+def family_scale(family: str) -> float:
+    """Coordinate scale c_family of ``cagp_scale_inputs`` (xs = (X - origin) * c_family / lengthscale)."""
+    import math
+
+    log2e = 1.0 / math.log(2.0)
+    return {"rbf": math.sqrt(0.5 * log2e), "matern12": log2e, "matern32": math.sqrt(3.0) * log2e,
+            "matern52": math.sqrt(5.0) * log2e}[family]
 F32, F64 = 0, 1
 
 
@@ -67,6 +76,11 @@ _SIGNATURES = {
     "cagp_ks_dense_bwd_ls_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int64, c_int32]),
     "cagp_ks_dense_bwd_ls": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
                                      c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cagp_cross_cov_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
+                                   c_void_p, c_int64, c_void_p]),
+    "cagp_cross_cov_bwd_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int64, c_int32]),
+    "cagp_cross_cov_bwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
+                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cagp_predict_ws_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "cagp_predict_moments": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -77,10 +91,11 @@ _lib = None
 # Launch accounting: number of kernels of THIS library launched (cuBLAS kernels not counted), and
 # optional CUDA-event timing of the pair kernels on the launching stream (bench.py sets PROFILE = []).
 LAUNCHES = 0
+CALLS = {}  # C entry point -> number of calls (tests use it to prove which native path ran)
 PROFILE = None
 _KERNELS_PER_CALL = {"cagp_ks_blocksparse_fwd_sym_peer": 1, "cagp_bounding_box": 1, "cagp_ks_dense_fwd": 1, "cagp_ks_dense_bwd_ls": 2, "cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
                      "cagp_project_rows": 1, "cagp_gram_mtm": 1, "cagp_assemble_cotangent": 1,
-                     "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1}
+                     "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1, "cagp_cross_cov_fwd": 1, "cagp_cross_cov_bwd": 2}
 
 
 class _timed:
@@ -92,6 +107,7 @@ class _timed:
     def __enter__(self):
         global LAUNCHES
         LAUNCHES += _KERNELS_PER_CALL.get(self.name, 0 if self.name.startswith("host:") else 1)
+        CALLS[self.name] = CALLS.get(self.name, 0) + 1
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -313,6 +329,37 @@ def ks_dense_bwd_ls(family, xs1, xs2, d, V, Ybar, lengthscale) -> torch.Tensor:
         _check(lib.cagp_ks_dense_bwd_ls(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(Vt), n, _ptr(Ybt), m, p,
                                         _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)), "cagp_ks_dense_bwd_ls")
     return ls_bar
+
+
+def cross_cov_fwd(family, xs1, xs2, d, lengthscale) -> torch.Tensor:
+    """C (m, n) = K'(X1, X2), materialised (unit variance)."""
+    _require_cuda(xs1, xs2)
+    m, n = xs1.shape[1], xs2.shape[1]
+    C = torch.empty((m, n), dtype=xs1.dtype, device=xs1.device)
+    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    kd = make_desc(family, ls, xs1.dtype)
+    with torch.cuda.device(xs1.device), _timed("cagp_cross_cov_fwd", xs1, m * n):
+        _check(load().cagp_cross_cov_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(C), n, _stream(xs1)),
+               "cagp_cross_cov_fwd")
+    return C
+
+
+def cross_cov_bwd(family, xs1, xs2, d, Cbar, lengthscale):
+    """(x2s_bar (padded_dim(d), n), ls_bar (n_lengthscale)): cotangents of the SCALED x2 coordinates and the lengthscale."""
+    Cbar = Cbar.contiguous()
+    _require_cuda(xs1, xs2, Cbar)
+    m, n = xs1.shape[1], xs2.shape[1]
+    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    kd = make_desc(family, ls, xs1.dtype)
+    lib = load()
+    ws_bytes = lib.cagp_cross_cov_bwd_ws_bytes(byref(kd), m, n, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs1.device)
+    x2s_bar = torch.empty((xs2.shape[0], n), dtype=xs1.dtype, device=xs1.device)
+    ls_bar = torch.empty(ls.numel(), dtype=xs1.dtype, device=xs1.device)
+    with torch.cuda.device(xs1.device), _timed("cagp_cross_cov_bwd", xs1, m * n):
+        _check(lib.cagp_cross_cov_bwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(Cbar), n, _ptr(x2s_bar),
+                                      _ptr(ls_bar), _ptr(ws), ws_bytes, _stream(xs1)), "cagp_cross_cov_bwd")
+    return x2s_bar, ls_bar
 
 
 def union_bounding_box(xs1: torch.Tensor, xs2: torch.Tensor) -> torch.Tensor:

@@ -298,6 +298,32 @@ int cagp_ks_dense_bwd_ls(const cagp_kernel_desc* kd, const void* xs1, int64_t m,
     return dense_ls_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, V, ldv, Ybar, ldyb, p, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int cagp_cross_cov_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                       int64_t ld2, int32_t d, void* C, int64_t ldc, cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs1 || !xs2 || !C) return fail(CAGP_ERR_INVALID, "cross_cov fwd: null pointer");
+    if (m < 1 || n < 1 || ld1 < m || ld2 < n || ldc < n) return fail(CAGP_ERR_INVALID, "cross_cov fwd: bad shape");
+    if (kd->dtype == CAGP_F64) return cross_fwd_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, C, ldc, (cudaStream_t)stream);
+    return cross_fwd_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, C, ldc, (cudaStream_t)stream);
+}
+
+size_t cagp_cross_cov_bwd_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d) {
+    if (check_desc(kd, d) || m < 1 || n < 1) return 0;
+    const bool ard = kd->n_lengthscale > 1;
+    return kd->dtype == CAGP_F64 ? cross_bwd_ws_bytes<double>(m, n, d, ard) : cross_bwd_ws_bytes<float>(m, n, d, ard);
+}
+
+int cagp_cross_cov_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                       int64_t ld2, int32_t d, const void* Cbar, int64_t ldc, void* x2s_bar, void* ls_bar, void* ws,
+                       size_t ws_bytes, cagp_stream_t stream) {
+    if (int rc = check_desc(kd, d)) return rc;
+    if (!xs1 || !xs2 || !Cbar || !x2s_bar || !ls_bar || !ws) return fail(CAGP_ERR_INVALID, "cross_cov bwd: null pointer");
+    if (m < 1 || n < 1 || ld1 < m || ld2 < n || ldc < n) return fail(CAGP_ERR_INVALID, "cross_cov bwd: bad shape");
+    if (kd->dtype == CAGP_F64)
+        return cross_bwd_impl<double>(kd, xs1, m, ld1, xs2, n, ld2, d, Cbar, ldc, x2s_bar, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+    return cross_bwd_impl<float>(kd, xs1, m, ld1, xs2, n, ld2, d, Cbar, ldc, x2s_bar, ls_bar, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t cagp_predict_ws_bytes(int32_t dtype, int64_t m, int32_t k) {
     const size_t es = dtype == CAGP_F64 ? 8 : 4;
     return (size_t)k * (size_t)m * es;

@@ -97,4 +97,14 @@ int dense_ls_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_
                   int64_t ld2, int d, const void* V, int64_t ldv, const void* Ybar, int64_t ldyb, int p, void* ls_bar,
                   void* ws, size_t ws_bytes, cudaStream_t stream);
 
+template <typename T>
+int cross_fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                   int64_t ld2, int d, void* C, int64_t ldc, cudaStream_t stream);
+template <typename T>
+size_t cross_bwd_ws_bytes(int64_t m, int64_t n, int d, bool ard);
+template <typename T>
+int cross_bwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2, int64_t n,
+                   int64_t ld2, int d, const void* Cbar, int64_t ldc, void* x2s_bar, void* ls_bar, void* ws,
+                   size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace cagp_host

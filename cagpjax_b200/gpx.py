@@ -232,10 +232,15 @@ def _leaf_slots(model) -> List[tuple]:
     slots = [(post.prior.kernel, "lengthscale"), (post.prior.kernel, "variance"), (post.likelihood, "obs_stddev")]
     if isinstance(post.prior.mean_function, Constant) and not isinstance(post.prior.mean_function, Zero):
         slots.append((post.prior.mean_function, "constant"))
-    if hasattr(model.policy, "nz_values"):
-        slots.append((model.policy, "nz_values"))
-    elif hasattr(model.policy, "actions"):
-        slots.append((model.policy, "actions"))
+    policy = model.policy
+    while policy is not None:  # wrappers (OrthogonalizationPolicy) hold their leaves in ``base_policy``
+        for attr in ("nz_values", "actions", "pseudo_inputs"):
+            if hasattr(policy, attr):
+                slots.append((policy, attr))
+        inner_kernel = getattr(policy, "kernel", None)
+        if inner_kernel is not None and inner_kernel is not post.prior.kernel:
+            slots += [(inner_kernel, "lengthscale"), (inner_kernel, "variance")]
+        policy = getattr(policy, "base_policy", None)
     return slots
 
 

@@ -137,7 +137,8 @@ class ComputationAwareGP:
         projection = None
         if isinstance(actions, BlockDiagonalSparse) and isinstance(cov_xx, LazyKernel) and cov_xx.is_gram:
             projection = cov_xx.project(actions, residual)
-        elif isinstance(actions, Dense) and isinstance(cov_xx, LazyKernel) and cov_xx.is_gram:
+        elif isinstance(actions, Dense) and isinstance(cov_xx, LazyKernel) and cov_xx.is_gram \
+                and isinstance(self.solver, Cholesky) and _fused_dense_statistics_ok(self.policy, actions, cov_xx):
             projection = cov_xx.project_dense(actions, residual)
         obs_cov_proj = congruence_transform(actions, obs_cov)
         cov_prior_proj = congruence_transform(actions, cov_prior)
@@ -217,6 +218,22 @@ class ComputationAwareGP:
         yt = state._residual
         return elbo_from_stats(proj.A, proj.B, proj.c, state.residual_proj, q, yt @ yt, x.shape[0], var, sigma,
                                self.solver.jitter)
+
+
+def _fused_dense_statistics_ok(policy, actions, cov_xx) -> bool:
+    """Whether the ELBO of a dense action matrix may be evaluated from the k-sized statistics A', B', c'.
+
+    The closed form contains w^T B' w and tr(P^-1 B'), which cancel catastrophically when S^T K^ S is badly
+    conditioned (raw pseudo-input actions S = K(X, Z): |w| ~ 1 / jitter).  It is therefore used only for actions
+    that are (scaled-)orthogonal by construction or declared well-conditioned by their policy, and for row-sharded
+    runs (where the statistics are what gets all-reduced).  Everything else takes the literal per-point route,
+    which shares the single memoised K S product between ``init`` and ``predict`` and costs the same kernel passes."""
+    from ..operators.annotations import ScaledOrthogonal
+    from ..ops import StiefelAnnotation, UnitaryAnnotation
+
+    if cov_xx.process_group is not None or getattr(policy, "fused_statistics", False):
+        return True
+    return any(actions.isa(a) for a in (StiefelAnnotation, UnitaryAnnotation, ScaledOrthogonal))
 
 
 def _elbo_fused_dense_impl(model, state):

@@ -23,6 +23,18 @@ class PSDAnnotation(Annotation):
     pass
 
 
+class SelfAdjointAnnotation(Annotation):
+    pass
+
+
+class UnitaryAnnotation(Annotation):
+    """Square operator with orthonormal columns (cola.Unitary)."""
+
+
+class StiefelAnnotation(Annotation):
+    """Tall operator with orthonormal columns (cola.Stiefel)."""
+
+
 class LinearOperator:
     """Abstract (m, n) linear operator; subclasses implement ``_matmat`` (and ``_rmatmat``)."""
 
@@ -254,6 +266,25 @@ def PSD(op: LinearOperator) -> LinearOperator:
     """Annotate ``op`` as positive semi-definite (cola.PSD)."""
     op.annotations.add(PSDAnnotation)
     return op
+
+
+def SelfAdjoint(op: LinearOperator) -> LinearOperator:
+    op.annotations.add(SelfAdjointAnnotation)
+    return op
+
+
+def Unitary(op: LinearOperator) -> LinearOperator:
+    op.annotations.add(UnitaryAnnotation)
+    return op
+
+
+def Stiefel(op: LinearOperator) -> LinearOperator:
+    op.annotations.add(StiefelAnnotation)
+    return op
+
+
+def I_like(op: LinearOperator) -> "Identity":
+    return Identity(op.shape, op.dtype, op.device)
 
 
 def lazify(A) -> LinearOperator:

@@ -15,7 +15,13 @@ from .base import AbstractBatchLinearSolverPolicy
 
 
 class DensePolicy(AbstractBatchLinearSolverPolicy):
-    """Actions given by a dense, learnable (n, n_actions) matrix."""
+    """Actions given by a dense, learnable (n, n_actions) matrix.
+
+    ``fused_statistics``: the matrix is expected to be well-conditioned (random Gaussian, orthogonal, ...), which
+    lets ``ComputationAwareGP`` evaluate the ELBO from the k-sized statistics of one fused pass (see
+    ``models.cagp._fused_dense_statistics_ok``); set it to False for ill-conditioned action matrices."""
+
+    fused_statistics = True
 
     def __init__(self, actions):
         self.actions = actions

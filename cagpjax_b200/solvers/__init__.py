@@ -2,5 +2,6 @@
 
 from .base import AbstractLinearSolver
 from .cholesky import Cholesky
+from .pseudoinverse import PseudoInverse
 
-__all__ = ["AbstractLinearSolver", "Cholesky"]
+__all__ = ["AbstractLinearSolver", "Cholesky", "PseudoInverse"]

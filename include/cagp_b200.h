@@ -195,6 +195,23 @@ int cagp_ks_dense_bwd_ls(const cagp_kernel_desc* kd, const void* xs1, int64_t m,
                          const void* Ybt, int64_t ldyb, int32_t p, void* ls_bar, void* ws,
                          size_t ws_bytes, cagp_stream_t stream);
 
+/* Materialised unit-variance cross-covariance C[i*ldc + j] = K'(x1_i, x2_j), (m, ldc >= n) row-major.  Replaces
+ * kernel.cross_covariance(train_inputs, pseudo_inputs) as called by PseudoInputPolicy.to_actions
+ * (policies/pseudoinput.py:68-74): the result is the dense action matrix fed to cagp_ks_dense_fwd. */
+int cagp_cross_cov_fwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2,
+                       int64_t n, int64_t ld2, int32_t d, void* C, int64_t ldc, cagp_stream_t stream);
+
+/* Reverse mode of cagp_cross_cov_fwd given Cbar (m, ldc), with respect to the x2 points (trainable
+ * pseudo-inputs) and the lengthscale(s):
+ *   x2s_bar[t*n + j] = sum_i Cbar_ij dK'(x1_i, x2_j) / d xs2[t][j]   (cagp_padded_dim(d), n), cotangent of the SCALED
+ *                      coordinates: the caller multiplies row t by c_family / lengthscale_t to get dL/dX2[j][t];
+ *   ls_bar[t]        = sum_ij Cbar_ij dK'(x1_i, x2_j) / d lengthscale_t   (through both operands).
+ * Deterministic (per-chunk partials in `ws`, cagp_cross_cov_bwd_ws_bytes() bytes, then one reduction). */
+size_t cagp_cross_cov_bwd_ws_bytes(const cagp_kernel_desc* kd, int64_t m, int64_t n, int32_t d);
+int cagp_cross_cov_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1, const void* xs2,
+                       int64_t n, int64_t ld2, int32_t d, const void* Cbar, int64_t ldc, void* x2s_bar,
+                       void* ls_bar, void* ws, size_t ws_bytes, cagp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

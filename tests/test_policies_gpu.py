@@ -1,0 +1,270 @@
+"""SURVEY 8(f) ranks 3-4 on the GPU: the materialised cross-covariance kernels, PseudoInputPolicy,
+LanczosPolicy (matrix-free matvecs through the pair kernels), OrthogonalizationPolicy and the PseudoInverse
+solver inside ComputationAwareGP - CUDA path vs the CPU oracle on the same seeded inputs."""
+
+import pytest
+import torch
+
+import cagpjax_b200 as cagp
+from cagpjax_b200 import _fused, _native, gpx
+from cagpjax_b200.linalg import OrthogonalizationMethod
+from cagpjax_b200.policies import LanczosPolicy, OrthogonalizationPolicy, PseudoInputPolicy
+from cagpjax_b200.solvers import Cholesky, PseudoInverse
+from oracle import cagp_oracle as O
+from oracle import cagp_oracle_ext as E
+from tests.util import KERNELS, make_data, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+
+
+def _inputs(m, n, d, ard, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(m, d, generator=g, dtype=torch.float64) * 4
+    Z = torch.rand(n, d, generator=g, dtype=torch.float64) * 4
+    ls = (0.7 + 0.5 * torch.rand(d, generator=g, dtype=torch.float64)) if ard else torch.tensor(0.9, dtype=torch.float64)
+    Cbar = torch.randn(m, n, generator=g, dtype=torch.float64)
+    return X, Z, ls, Cbar
+
+
+# ------------------------------------------------------------------------------------------------
+# cagp_cross_cov_fwd / cagp_cross_cov_bwd through the C ABI
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("family", O.KERNEL_FAMILIES)
+@pytest.mark.parametrize("m,n,d,ard", [(1, 1, 1, False), (7, 3, 1, False), (130, 5, 2, True), (1037, 129, 3, True),
+                                       (300, 64, 8, False), (257, 40, 16, True), (90, 17, 32, True), (5000, 260, 3, False)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_cross_covariance_kernels_match_oracle(family, m, n, d, ard, dtype):
+    X, Z, ls, Cbar = _inputs(m, n, d, ard)
+    Zo, lso = Z.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    Co = O.cross_covariance(family, X, Zo, lso, torch.tensor(1.0, dtype=torch.float64))
+    gZ, gls = torch.autograd.grad((Co * Cbar).sum(), [Zo, lso])
+
+    to = lambda t: t.to(device=DEV, dtype=dtype)
+    Zg, lsg = to(Z).requires_grad_(True), to(ls).requires_grad_(True)
+    before = dict(_native.CALLS)
+    C = _fused.cross_covariance(family, to(X), Zg, lsg)
+    hZ, hls = torch.autograd.grad((C * to(Cbar)).sum(), [Zg, lsg])
+    assert _native.CALLS["cagp_cross_cov_fwd"] == before.get("cagp_cross_cov_fwd", 0) + 1
+    assert _native.CALLS["cagp_cross_cov_bwd"] == before.get("cagp_cross_cov_bwd", 0) + 1
+    tol = TOL[dtype]
+    assert C.shape == (m, n) and C.dtype == dtype
+    assert rel_err(C, Co) < tol
+    # sums of m*n signed terms: scale the tolerance by the size of the summands
+    scale = float((Cbar.abs().unsqueeze(-1) * torch.ones(1)).sum() / max(m * n, 1)) + 1.0
+    gtol = tol * 50 if dtype == torch.float64 else 5e-3
+    assert float((hZ.double().cpu() - gZ).abs().max()) <= gtol * max(float(gZ.abs().max()), scale)
+    assert float((hls.double().cpu() - gls).abs().max()) <= gtol * max(float(gls.abs().max()), scale)
+
+
+def test_cross_covariance_rejects_cpu_tensors():
+    X, Z, ls, _ = _inputs(5, 2, 1, False)
+    with pytest.raises(_native.NativeLibraryError):
+        _fused.cross_covariance("rbf", X, Z, ls)
+
+
+# ------------------------------------------------------------------------------------------------
+# model-level parity
+# ------------------------------------------------------------------------------------------------
+def make_model(family, n, d, policy_fn, solver, *, ard=False, seed=0, dtype=torch.float64, mean_constant=0.5,
+               obs_stddev=0.2, variance=1.3):
+    x, y = make_data(n, d, seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    ls = (0.7 + 0.5 * torch.rand(d, generator=g, dtype=torch.float64)) if ard else torch.tensor(0.9, dtype=torch.float64)
+    to = lambda t: torch.as_tensor(t, dtype=torch.float64).to(device=DEV, dtype=dtype)
+    kernel = KERNELS[family](lengthscale=to(ls), variance=to(variance), compute_engine=cagp.computations.LazyKernelComputation())
+    prior = gpx.Prior(kernel=kernel, mean_function=gpx.Constant(to(mean_constant)))
+    lik = gpx.Gaussian(n, obs_stddev=to(obs_stddev))
+    data = gpx.Dataset(to(x), to(y).reshape(-1, 1))
+    policy = policy_fn(kernel, data)
+    model = cagp.ComputationAwareGP(prior * lik, policy, solver)
+    leaves = dict(lengthscale=ls, variance=torch.tensor(variance, dtype=torch.float64),
+                  obs_stddev=torch.tensor(obs_stddev, dtype=torch.float64),
+                  mean_constant=torch.tensor(mean_constant, dtype=torch.float64))
+    return model, data, leaves, x, y
+
+
+def oracle_value_and_grad(fn, leaves):
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
+    val = fn(**q)
+    grads = torch.autograd.grad(val, list(q.values()), allow_unused=True)
+    return val.detach(), {k: (torch.zeros_like(v) if g is None else g) for (k, v), g in zip(q.items(), grads)}
+
+
+def solver_kwargs(solver):
+    if isinstance(solver, PseudoInverse):
+        return dict(solver="pinv", rtol=solver.rtol)
+    return dict(solver="cholesky", jitter=solver.jitter)
+
+
+NAMES = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev", "constant": "mean_constant",
+         "pseudo_inputs": "pseudo_inputs"}
+
+
+def check_grads(grads, ograds, tol, expect):
+    seen = set()
+    for name, g in grads.items():
+        key = NAMES[name.split(".")[1]]
+        ref = ograds[key].reshape(-1)
+        err = float((-g.reshape(-1).double().cpu() - ref).abs().max())
+        assert err <= tol * max(float(ref.abs().max()), 1.0), (name, err)
+        seen.add(key)
+    assert seen == set(expect)
+
+
+def neg_elbo(model, data):
+    return -model.elbo(model.init(data, key=0))
+
+
+@pytest.mark.parametrize("family,n,d,M,ard", [("rbf", 300, 1, 12, False), ("rbf", 1037, 3, 20, True),
+                                              ("matern32", 700, 2, 16, False), ("matern52", 523, 8, 24, True),
+                                              ("matern12", 400, 3, 13, False)])
+@pytest.mark.parametrize("solver", [Cholesky(1e-6), PseudoInverse()], ids=["cholesky", "pinv"])
+def test_pseudo_input_policy_elbo_and_gradients(family, n, d, M, ard, solver):
+    g = torch.Generator().manual_seed(5)
+    Z = torch.rand(M, d, generator=g, dtype=torch.float64) * 4
+    model, data, leaves, x, y = make_model(
+        family, n, d, lambda kernel, data: PseudoInputPolicy(gpx.Real(Z.to(DEV)), data, kernel), solver, ard=ard)
+    # actions are the cross-covariance (tests/test_policies.py:335-345 of the reference)
+    with torch.no_grad():
+        S = model.policy.to_actions(None).to_dense()
+        So = E.pseudo_input_actions(family, x, Z, leaves["lengthscale"], leaves["variance"])
+        assert S.shape == (n, M) and rel_err(S, So) < 1e-10
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+
+    def oracle(lengthscale, variance, obs_stddev, mean_constant, pseudo_inputs):
+        S = E.pseudo_input_actions(family, x, pseudo_inputs, lengthscale, variance)
+        return E.elbo_dense_actions(family, x, y, lengthscale, variance, obs_stddev, mean_constant, S,
+                                    **solver_kwargs(solver))[0]
+
+    oval, ograds = oracle_value_and_grad(oracle, dict(leaves, pseudo_inputs=Z))
+    # S = K(X, Z) is ill-conditioned (that is why the reference recommends orthogonalising it): the k x k
+    # systems amplify rounding, so the comparison is at 1e-7 rather than the hot path's 1e-10
+    # ... and 12 pseudo-inputs on a 1-D interval of 4 lengthscales push eigenvalues of S^T K^ S through the jitter /
+    # pseudo-inverse cutoff, where the result is discontinuous in the last bits of the input
+    worst = d == 1
+    vtol = (1e-4 if isinstance(solver, PseudoInverse) else 1e-6) if worst else 1e-7
+    assert rel_err(-val, oval) < vtol
+    if not (worst and isinstance(solver, PseudoInverse)):
+        check_grads(grads, ograds, 1e-3 if worst else 1e-5,
+                    ["lengthscale", "variance", "obs_stddev", "mean_constant", "pseudo_inputs"])
+
+
+@pytest.mark.parametrize("method,n_reortho", [(OrthogonalizationMethod.QR, 0), (OrthogonalizationMethod.CGS, 1),
+                                              (OrthogonalizationMethod.MGS, 1)])
+@pytest.mark.parametrize("family,n,d,M", [("rbf", 600, 2, 16), ("matern32", 1037, 3, 20)])
+def test_orthogonalized_pseudo_inputs_elbo_and_gradients(method, n_reortho, family, n, d, M):
+    g = torch.Generator().manual_seed(6)
+    Z = torch.rand(M, d, generator=g, dtype=torch.float64) * 4
+    solver = Cholesky(1e-6)
+    model, data, leaves, x, y = make_model(
+        family, n, d, lambda kernel, data: OrthogonalizationPolicy(
+            PseudoInputPolicy(gpx.Real(Z.to(DEV)), data, kernel), method=method, n_reortho=n_reortho), solver)
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    ortho = {OrthogonalizationMethod.QR: E.orthogonalize_qr, OrthogonalizationMethod.CGS: E.orthogonalize_cgs,
+             OrthogonalizationMethod.MGS: E.orthogonalize_mgs}[method]
+
+    def oracle(lengthscale, variance, obs_stddev, mean_constant, pseudo_inputs):
+        S = ortho(E.pseudo_input_actions(family, x, pseudo_inputs, lengthscale, variance), n_reortho)
+        return E.elbo_dense_actions(family, x, y, lengthscale, variance, obs_stddev, mean_constant, S,
+                                    **solver_kwargs(solver))[0]
+
+    oval, ograds = oracle_value_and_grad(oracle, dict(leaves, pseudo_inputs=Z))
+    assert rel_err(-val, oval) < 1e-9
+    check_grads(grads, ograds, 1e-6, ["lengthscale", "variance", "obs_stddev", "mean_constant", "pseudo_inputs"])
+
+
+def test_orthogonalization_of_replicated_pseudo_inputs():
+    """Rank-deficient actions (tests/test_policies.py:422-468 of the reference)."""
+    n, M, d = 20, 10, 1
+    g = torch.Generator().manual_seed(7)
+    Zu = torch.randn(M - M // 2, d, generator=g, dtype=torch.float64)
+    Z = torch.cat([Zu, Zu[: M // 2]], dim=0)
+    X = torch.randn(n, d, generator=g, dtype=torch.float64).to(DEV)
+    kernel = gpx.RBF(lengthscale=torch.ones(d, dtype=torch.float64, device=DEV),
+                     variance=torch.tensor(1.0, dtype=torch.float64, device=DEV))
+    base = PseudoInputPolicy(Z.to(DEV), X, kernel)
+    op = kernel.gram(X)
+    base_actions = base.to_actions(op).to_dense()
+    for method, nr in [(OrthogonalizationMethod.QR, 0), (OrthogonalizationMethod.CGS, 1), (OrthogonalizationMethod.MGS, 1)]:
+        actions = OrthogonalizationPolicy(base, method=method, n_reortho=nr).to_actions(op)
+        assert actions.shape == (n, M) and actions.dtype == torch.float64
+        Q = actions.to_dense()
+        assert not torch.allclose(Q, base_actions)
+        assert torch.allclose(Q @ (Q.T @ base_actions), base_actions, atol=1e-8)
+
+
+@pytest.mark.parametrize("family,n,d,k", [("rbf", 300, 1, 5), ("matern32", 700, 3, 8), ("rbf", 1037, 3, 10)])
+# grad_rtol: Lanczos actions are orthonormal, so the projected noise covariance sigma^2 S^T S has a (numerically)
+# repeated eigenvalue - the documented case for a non-None grad_rtol (solvers/pseudoinverse.py:35-40 of the reference)
+@pytest.mark.parametrize("solver", [Cholesky(1e-6), PseudoInverse(grad_rtol=1e-9)], ids=["cholesky", "pinv"])
+def test_lanczos_policy_elbo_and_gradients(family, n, d, k, solver):
+    model, data, leaves, x, y = make_model(family, n, d, lambda kernel, data: LanczosPolicy(n_actions=k), solver)
+    before = _native.CALLS.get("cagp_ks_blocksparse_fwd", 0) + _native.CALLS.get("cagp_ks_blocksparse_fwd_sym", 0)
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    after = _native.CALLS.get("cagp_ks_blocksparse_fwd", 0) + _native.CALLS.get("cagp_ks_blocksparse_fwd_sym", 0)
+    assert after - before >= k  # every Lanczos matvec is a pass of the pair kernels
+    v0 = torch.randn(n, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+
+    def oracle(lengthscale, variance, obs_stddev, mean_constant):
+        Khat = O.cross_covariance(family, x, x, lengthscale, variance) + obs_stddev**2 * torch.eye(n, dtype=torch.float64)
+        S = E.lanczos_eigh(Khat, k, v0)[1]
+        return E.elbo_dense_actions(family, x, y, lengthscale, variance, obs_stddev, mean_constant, S,
+                                    **solver_kwargs(solver))[0]
+
+    oval, ograds = oracle_value_and_grad(oracle, leaves)
+    assert rel_err(-val, oval) < 1e-9
+    check_grads(grads, ograds, 1e-6, ["lengthscale", "variance", "obs_stddev", "mean_constant"])
+
+
+@pytest.mark.parametrize("policy_kind", ["lanczos", "pseudo", "blocksparse"])
+def test_predict_with_pseudoinverse_solver(policy_kind):
+    family, n, d, k = "rbf", 400, 2, 6
+    solver = PseudoInverse()
+    g = torch.Generator().manual_seed(8)
+    Z = torch.rand(k, d, generator=g, dtype=torch.float64) * 4
+    s = O.normalize_by_blocks(torch.randn(n, generator=g, dtype=torch.float64), k)
+    policy_fn = {"lanczos": lambda kernel, data: LanczosPolicy(n_actions=k),
+                 "pseudo": lambda kernel, data: PseudoInputPolicy(Z.to(DEV), data, kernel),
+                 "blocksparse": lambda kernel, data: cagp.BlockSparsePolicy(n_actions=k, nz_values=s.to(DEV))}[policy_kind]
+    model, data, leaves, x, y = make_model(family, n, d, policy_fn, solver)
+    ls, var = leaves["lengthscale"], leaves["variance"]
+    if policy_kind == "lanczos":
+        Khat = O.cross_covariance(family, x, x, ls, var) + leaves["obs_stddev"] ** 2 * torch.eye(n, dtype=torch.float64)
+        S = E.lanczos_eigh(Khat, k, torch.randn(n, generator=torch.Generator().manual_seed(0), dtype=torch.float64))[1]
+    elif policy_kind == "pseudo":
+        S = E.pseudo_input_actions(family, x, Z, ls, var)
+    else:
+        S = O.bds_dense(s, k)
+    zt = torch.rand(33, d, generator=g, dtype=torch.float64) * 4
+    with torch.no_grad():
+        st = model.init(data, key=0)
+        q = model.predict(st, zt.to(DEV))
+        elbo = model.elbo(st)
+        oe, om, ov = E.elbo_dense_actions(family, x, y, ls, var, leaves["obs_stddev"], leaves["mean_constant"], S,
+                                          solver="pinv", z=zt)
+    tol = 1e-6 if policy_kind == "pseudo" else 1e-9
+    assert rel_err(elbo, oe) < tol
+    assert rel_err(q.mean, om) < tol * 10
+    assert rel_err(q.variance, ov) < tol * 10
+    assert q.scale.shape == (33, 33)
+    cov = q.scale.to_dense()
+    assert rel_err(torch.diagonal(cov), ov) < tol * 10
+
+
+def test_fit_with_pseudo_inputs_improves_elbo():
+    """The README training loop (README.md:57-68) with trainable pseudo-inputs behind an orthogonalising wrapper."""
+    n, d, M = 500, 1, 8
+    g = torch.Generator().manual_seed(3)
+    Z = torch.linspace(0.2, 3.8, M, dtype=torch.float64).reshape(-1, 1)
+    model, data, *_ = make_model(
+        "rbf", n, d, lambda kernel, data: OrthogonalizationPolicy(PseudoInputPolicy(gpx.Real(Z.to(DEV)), data, kernel)),
+        Cholesky(1e-6))
+    z0 = gpx.unwrap(model.policy.base_policy.pseudo_inputs).clone()
+    model, history = gpx.fit(model=model, objective=lambda m, dd: -m.elbo(m.init(dd)), train_data=data, optim="adam",
+                             num_iters=30, learning_rate=0.05)
+    assert torch.isfinite(history).all()
+    assert float(history[-1]) < float(history[0])
+    assert not torch.equal(gpx.unwrap(model.policy.base_policy.pseudo_inputs), z0)
