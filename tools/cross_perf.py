@@ -3,7 +3,10 @@
 The forward writes the (m, n) matrix once (algorithmic bytes m*n*itemsize); the backward reads the cotangent once.
 usage: python tools/cross_perf.py [m] [n] [d]"""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 import torch
 
