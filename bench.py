@@ -50,9 +50,11 @@ def pair_flops(family: str, d: int, backward: bool) -> int:
 FP64_PEAK_TFLOPS = 33.9  # measured DFMA stream on this pool's B200 (profiles/r01_fp64_peaks.json); nominal 37.2
 
 # fp64 issue slots actually executed per ORDERED pair by each pair kernel (counted in the SASS of the
-# d = 3 RBF instances; the symmetric kernels evaluate each unordered pair once = half per ordered pair).
+# d = 3 RBF instances; the symmetric kernels evaluate each unordered pair once = half per ordered pair, and
+# run the expanded-distance form on this workload: 12 slots per unordered pair forward, 16 backward).
 FP64_SLOTS_PER_PAIR = {"cagp_ks_blocksparse_fwd": 14.0, "cagp_ks_blocksparse_bwd": 16.0,
-                       "cagp_ks_blocksparse_fwd_sym": 7.5, "cagp_ks_blocksparse_bwd_sym": 9.0}
+                       "cagp_ks_blocksparse_fwd_sym": 6.0, "cagp_ks_blocksparse_fwd_sym_peer": 6.0,
+                       "cagp_ks_blocksparse_bwd_sym": 8.0}
 
 
 def synth(cfg, device, dtype):

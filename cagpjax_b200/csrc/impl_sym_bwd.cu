@@ -44,7 +44,7 @@ int sym_bwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                         const int gy = sym_choose_groups(a.til, gx);
                         nparts = gx * gy;
                         if (ws_bytes < (size_t)nparts * NLS * sizeof(T)) return fail(CAGP_ERR_WORKSPACE, "ks sym bwd workspace too small");
-                        const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NC * 9)) * sizeof(T);
+                        const size_t smem = (cagp::SymCanExpand<T, FAM, SPREAD>::kTabElems + (size_t)JC * (D + 2 + NC * 9)) * sizeof(T);
                         auto kern = cagp::ks_sym_bwd_kernel<T, D, FAM, ARD, R, JC, SPREAD>;
                         if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                         kern<<<dim3((unsigned)gx, (unsigned)gy), a.til.nthreads, smem, stream>>>(a);

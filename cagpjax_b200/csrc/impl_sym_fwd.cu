@@ -40,7 +40,7 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 auto launch = [&](auto sp) {
                     constexpr bool SPREAD = decltype(sp)::value;
                     constexpr int NC = SPREAD ? R : 1;
-                    const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * (D + 1 + NC * 8)) * sizeof(T);
+                    const size_t smem = (cagp::SymCanExpand<T, FAM, SPREAD>::kTabElems + (size_t)JC * (D + 2 + NC * 8)) * sizeof(T);
                     auto kern = cagp::ks_sym_fwd_kernel<T, D, FAM, R, JC, SPREAD>;
                     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     kern<<<dim3((unsigned)gx, (unsigned)gy), a.til.nthreads, smem, stream>>>(a);

@@ -51,6 +51,22 @@ struct ExpTab<double> {
         return (unsigned)__cvta_generic_to_shared(tab);
     }
 };
+// Second layout for the EXPANDED-form RBF kernels, whose fp64 work per pair is small enough that the shared-memory
+// pipe (table lookups with random bank conflicts, ~5 wavefronts per warp) becomes the limiter: 256 cells of width
+// 2^-8, each replicated 16 times so that lane l reads copy l mod 16.  A 64-bit warp load is served per half-warp,
+// and the 16 lanes of a half-warp then hit 16 different bank pairs: always 2 wavefronts (exp2neg16).
+constexpr int kExpTab16Bits = 8;
+constexpr int kExpTab16Cells = 1 << kExpTab16Bits;
+constexpr int kExpTab16Elems = kExpTab16Cells * 16;  // 32 KB of doubles
+__device__ __forceinline__ unsigned exptab16_load(double* tab, int tid, int nthreads) {
+    for (int i = tid; i < kExpTab16Elems; i += nthreads) {
+        const int j = i >> 4;
+        const double v = g_exp2_tab[j << (kExpTabBits - kExpTab16Bits)];  // 2^(-j/256)
+        tab[i] = __hiloint2double(__double2hiint(v) + (j << 12), __double2loint(v));
+    }
+    return (unsigned)__cvta_generic_to_shared(tab) + ((unsigned)(tid & 15) << 3);  // per-lane copy
+}
+
 template <>
 struct ExpTab<float> {
     static constexpr int kSmemElems = 0;
@@ -94,6 +110,33 @@ __device__ __forceinline__ double exp2neg(double u, unsigned tab_s) {
     asm("mad.lo.s32 %0, %1, -512, %2;" : "=r"(thi) : "r"(lo), "r"(__double2hiint(tv)));
     return __hiloint2double(thi, __double2loint(tv)) * p;
 }
+
+// 2^(-u) for |u| < 2000 from the replicated 256-cell table (exptab16_load); no clamp: callers hold a launch-wide
+// range proof.  magic = 1.5 * 2^44 has ulp 2^-8, so |f| <= 2^-9.  The cubic is the Chebyshev-node interpolant of
+// 2^(-f) on [-2^-9, 2^-9] (near-minimax, max relative error 1.75e-14, equi-oscillating - against 1.4e-13 for the
+// Taylor cubic); a quartic would reach 4e-17 for one more DFMA per evaluation, which costs 5 % of the kernel for
+// accuracy the 1e-10 parity bar does not need.  fp64 pipe cost: 3 DADD + 3 DFMA + 1 DMUL.
+__device__ __forceinline__ double exp2neg16(double u, unsigned tab_lane) {
+    constexpr double kMagic = 26388279066624.0;  // 1.5 * 2^44
+    const double t = u + kMagic;
+    const unsigned lo = (unsigned)__double2loint(t);
+    const double f = u - (t - kMagic);
+    unsigned idx, addr;
+    asm("and.b32 %0, %1, 255;" : "=r"(idx) : "r"(lo));
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(idx), "r"(tab_lane));
+    double tv;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(addr));
+    constexpr double c0 = 0.999999999999982504724;
+    constexpr double c1 = -0.693147180559942884057;
+    constexpr double c2 = 0.2402265436493534809523;
+    constexpr double c3 = -0.05550411375117055438833;
+    const double p = fma(f, fma(f, fma(f, c3, c2), c1), c0);
+    // table high words carry + (j << 12); subtracting lo << 12 = (n << 20) + (j << 12) leaves 2^-n * T[j]
+    int thi;
+    asm("mad.lo.s32 %0, %1, -4096, %2;" : "=r"(thi) : "r"(lo), "r"(__double2hiint(tv)));
+    return __hiloint2double(thi, __double2loint(tv)) * p;
+}
+__device__ __forceinline__ float exp2neg16(float u, unsigned) { return u; }  // never used (fp64 only)
 
 template <bool SAFE = false>
 __device__ __forceinline__ float exp2neg(float u, unsigned) {
@@ -194,6 +237,23 @@ __device__ __forceinline__ bool launch_is_safe(const T* __restrict__ bbox) {
         qm = fma(w, w, qm);
     }
     return FAM == RBF ? (qm < T(990)) : (qm < T(990) * T(990));  // false for NaN
+}
+
+// Launch-wide proof for the EXPANDED distance form of the RBF kernels (fp64): with na = |a|^2, nb = |b|^2,
+//   K' = 2^(-|a - b|^2) = 2^(-na) * 2^(-(nb - 2 a.b)),
+// so the per-pair work is a D-term FMA chain started at nb (D fp64 slots instead of 2 D) and the row factor
+// 2^(-na) is applied once per row.  Valid when every point of the launch has |x|^2 < 300: the exponent
+// nb - 2 a.b then lies in (-300, 900) (no clamp, no overflow) and its rounding error, a few ulp of 900, is
+// below 1e-12 relative in K' (the coordinates are origin-shifted by cagp_scale_inputs).
+template <typename T, int D, int FAM>
+__device__ __forceinline__ bool launch_is_expandable(const T* __restrict__ bbox) {
+    if (sizeof(T) == 4 || bbox == nullptr || FAM != RBF) return false;
+    T s = T(0);
+    for (int t = 0; t < D; ++t) {
+        const T m = fmax(fabs(bbox[t]), fabs(bbox[D + t]));
+        s = fma(m, m, s);
+    }
+    return s < T(300);  // false for NaN
 }
 
 // host+device: coordinate scale and gradient constant per family

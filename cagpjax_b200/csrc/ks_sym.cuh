@@ -75,6 +75,15 @@ struct SymTiling {
     }
 };
 
+// The expanded-distance RBF form (kernel_math.cuh: launch_is_expandable, exp2neg16) is compiled into the fp64 RBF
+// kernels of the SINGLE shape only: its replicated exp2 table needs 32 KB of shared memory instead of 16 KB, which
+// would cost the SPREAD shape (large column accumulators) a resident CTA.
+template <typename T, int FAM, bool SPREAD>
+struct SymCanExpand {
+    static constexpr bool value = sizeof(T) == 8 && FAM == RBF && !SPREAD;
+    static constexpr int kTabElems = value ? kExpTab16Elems : ExpTab<T>::kSmemElems;
+};
+
 constexpr int kMaxPeers = 16;
 // column tails of at most this many columns use the broadcast formulation instead of a 32-step ring
 constexpr int kSymTailBroadcast = 20;
@@ -158,20 +167,30 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
     constexpr int NWMAX = 8;
     constexpr int NC = SPREAD ? R : 1;  // independent column accumulators (one per row block)
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool CAN_EXPAND = SymCanExpand<T, FAM, SPREAD>::value;
     T* tab = reinterpret_cast<T*>(smem_raw);
-    T* xc = tab + ExpTab<T>::kSmemElems;  // [D][JC]
+    T* xc = tab + SymCanExpand<T, FAM, SPREAD>::kTabElems;  // [D][JC]
     T* sc = xc + D * JC;                  // [JC]
-    T* colacc = sc + JC;                  // [NC][NWMAX][JC]
+    T* nbc = sc + JC;                     // [JC]  |x_j|^2 of the staged columns (expanded form only)
+    T* colacc = nbc + JC;                 // [NC][NWMAX][JC]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
-    const unsigned tab_s = ExpTab<T>::load(tab, tid, nthreads);
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
+    // uniform: expanded distance form with the replicated exp2 table (kernel_math.cuh)
+    const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);
+    unsigned tab_s;
+    if constexpr (CAN_EXPAND) {
+        tab_s = expand ? exptab16_load(tab, tid, nthreads) : ExpTab<T>::load(tab, tid, nthreads);
+    } else {
+        tab_s = ExpTab<T>::load(tab, tid, nthreads);
+    }
     const SymTiling& til = p.til;
     const BlockLayout& lay = til.lay;
     const SymRows<R, SPREAD> pl = SymRows<R, SPREAD>::make(til, blockIdx.x, tid, nthreads);
 
-    T ar[R][D], srow[R];
+    T ar[R][D], srow[R], erow[R];
     int64_t irow[R];
     bool valid[R];
+    __syncthreads();  // the exp2 table is used below (expanded form)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const bool bok = pl.block_ok(r);
@@ -183,6 +202,16 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
 #pragma unroll
         for (int t = 0; t < D; ++t) ar[r][t] = p.xs[t * p.ld + irow[r]];
         srow[r] = valid[r] ? p.s[irow[r]] : T(0);
+        erow[r] = T(1);
+        if constexpr (CAN_EXPAND) {
+            if (expand) {  // row factor 2^(-|a|^2); the column partials take s_i 2^(-|a|^2)
+                T na = T(0);
+#pragma unroll
+                for (int t = 0; t < D; ++t) na = fma(ar[r][t], ar[r][t], na);
+                erow[r] = exp2neg16(na, tab_s);
+                srow[r] *= erow[r];
+            }
+        }
     }
     const int n_off0 = til.n_off0();
     const int off_begin = blockIdx.y * til.offs_per_cta;
@@ -214,25 +243,45 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
             for (int idx = tid; idx < clp; idx += nthreads) {
                 const bool in = idx < cl;
                 const int64_t j = j0 + c0 + (in ? idx : 0);
+                T nb = T(0);
 #pragma unroll
-                for (int t = 0; t < D; ++t) xc[t * JC + idx] = in ? p.xs[t * p.ld + j] : T(0);
+                for (int t = 0; t < D; ++t) {
+                    const T v = in ? p.xs[t * p.ld + j] : T(0);
+                    nb = fma(v, v, nb);
+                    xc[t * JC + idx] = expand ? T(-2) * v : v;
+                }
+                nbc[idx] = nb;
                 sc[idx] = in ? p.s[j] : T(0);
             }
             __syncthreads();
-            auto sweep = [&](auto safe_c) {
-                constexpr bool SAFE = decltype(safe_c)::value;
+            auto sweep = [&](auto mode_c) {
+                constexpr int MODE = decltype(mode_c)::value;  // 0 general, 1 safe range, 2 safe + expanded form
+                constexpr bool SAFE = MODE >= 1;
                 // one (thread, column) step: R kernel values feed the row sums and the column partials
                 auto pair_step = [&](int cidx, T (&cacc)[NC]) {
                     T xb[D];
 #pragma unroll
                     for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
                     const T w = sc[cidx];
+                    if constexpr (MODE == 2) {
+                        const T nb = nbc[cidx];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const T q = sqdist<T, D>(ar[r], xb);
-                        const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
-                        racc[r] = fma(kv, w, racc[r]);
-                        cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                        for (int r = 0; r < R; ++r) {
+                            T u = nb;  // |b|^2 - 2 a.b  (xb holds -2 b)
+#pragma unroll
+                            for (int tt = 0; tt < D; ++tt) u = fma(ar[r][tt], xb[tt], u);
+                            const T kv = exp2neg16(u, tab_s);  // K' / 2^(-|a|^2)
+                            racc[r] = fma(kv, w, racc[r]);
+                            cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const T q = sqdist<T, D>(ar[r], xb);
+                            const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
+                            racc[r] = fma(kv, w, racc[r]);
+                            cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                        }
                     }
                 };
                 for (int sub = 0; sub < clp; sub += 32) {
@@ -270,10 +319,16 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                 }
             };
             if constexpr (sizeof(T) == 8) {
-                if (safe) sweep(std::true_type{});
-                else sweep(std::false_type{});
+                if constexpr (CAN_EXPAND) {
+                    if (expand) sweep(std::integral_constant<int, 2>{});
+                    else if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                } else {
+                    if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                }
             } else {
-                sweep(std::false_type{});
+                sweep(std::integral_constant<int, 0>{});
             }
             __syncthreads();
             // column sums: Mt[a_c][j in b], for the row blocks that own a symmetric (off != 0) tile
@@ -292,7 +347,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (mine[SPREAD ? r : 0] && valid[r]) row_panel[(int64_t)b * p.ldm + irow[r]] = racc[r];
+            if (mine[SPREAD ? r : 0] && valid[r]) row_panel[(int64_t)b * p.ldm + irow[r]] = racc[r] * erow[r];
     }
 }
 
@@ -302,22 +357,31 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
     constexpr int NC = SPREAD ? R : 1;
     constexpr int NLS = ARD ? D : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool CAN_EXPAND = SymCanExpand<T, FAM, SPREAD>::value && !ARD;  // isotropic: only q is needed, not q_t
     T* tab = reinterpret_cast<T*>(smem_raw);
-    T* xc = tab + ExpTab<T>::kSmemElems;  // [D][JC]
+    T* xc = tab + SymCanExpand<T, FAM, SPREAD>::kTabElems;  // [D][JC]
     T* sc = xc + D * JC;                  // [JC]
-    T* gc = sc + JC;                      // [NC][JC]   G[j, a_c] for the columns
+    T* nbc = sc + JC;                     // [JC]  |x_j|^2 of the staged columns (expanded form only)
+    T* gc = nbc + JC;                     // [NC][JC]   G[j, a_c] for the columns
     T* colacc = gc + NC * JC;             // [NC][NWMAX][JC]
     __shared__ T red[NWMAX][NLS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
-    const unsigned tab_s = ExpTab<T>::load(tab, tid, nthreads);
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
+    const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);  // uniform, see the forward kernel
+    unsigned tab_s;
+    if constexpr (CAN_EXPAND) {
+        tab_s = expand ? exptab16_load(tab, tid, nthreads) : ExpTab<T>::load(tab, tid, nthreads);
+    } else {
+        tab_s = ExpTab<T>::load(tab, tid, nthreads);
+    }
     const SymTiling& til = p.til;
     const BlockLayout& lay = til.lay;
     const SymRows<R, SPREAD> pl = SymRows<R, SPREAD>::make(til, blockIdx.x, tid, nthreads);
 
-    T ar[R][D], srow[R];
+    T ar[R][D], srow[R], erow[R], narow[R];
     int64_t irow[R];
     bool valid[R];
+    __syncthreads();  // the exp2 table is used below (expanded form)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const bool bok = pl.block_ok(r);
@@ -329,6 +393,15 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
 #pragma unroll
         for (int t = 0; t < D; ++t) ar[r][t] = p.xs[t * p.ld + irow[r]];
         srow[r] = valid[r] ? p.s[irow[r]] : T(0);
+        erow[r] = T(1);
+        narow[r] = T(0);
+        if constexpr (CAN_EXPAND) {
+            if (expand) {  // K' = erow * 2^(-(nb - 2 a.b)); every accumulator below carries the 1 / erow scale
+#pragma unroll
+                for (int t = 0; t < D; ++t) narow[r] = fma(ar[r][t], ar[r][t], narow[r]);
+                erow[r] = exp2neg16(narow[r], tab_s);
+            }
+        }
     }
     T sacc[R], l2[R][NLS], ltot[NLS];
 #pragma unroll
@@ -358,6 +431,7 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             grow[r] = (mine[SPREAD ? r : 0] && valid[r]) ? p.Gt[(int64_t)b * p.ldg + irow[r]] : T(0);  // G[i, b]
+            grow[r] *= erow[r];  // expanded form: the pair values are K' / erow (erow == 1 otherwise)
 #pragma unroll
             for (int t = 0; t < NLS; ++t) l1[r][t] = T(0);
         }
@@ -368,21 +442,46 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
             for (int idx = tid; idx < clp; idx += nthreads) {
                 const bool in = idx < cl;
                 const int64_t j = j0 + c0 + (in ? idx : 0);
+                T nb = T(0);
 #pragma unroll
-                for (int t = 0; t < D; ++t) xc[t * JC + idx] = in ? p.xs[t * p.ld + j] : T(0);
+                for (int t = 0; t < D; ++t) {
+                    const T v = in ? p.xs[t * p.ld + j] : T(0);
+                    nb = fma(v, v, nb);
+                    xc[t * JC + idx] = expand ? T(-2) * v : v;
+                }
+                nbc[idx] = nb;
                 sc[idx] = in ? p.s[j] : T(0);
 #pragma unroll
                 for (int c = 0; c < NC; ++c)  // column weights G[j, a_c]; zero for idle row blocks and (diagonal
                     gc[c * JC + idx] = (in && mine[c]) ? p.Gt[(int64_t)pl.a_of(c) * p.ldg + j] : T(0);  // handled below)
             }
             __syncthreads();
-            auto sweep = [&](auto safe_c) {
-                constexpr bool SAFE = decltype(safe_c)::value;
+            auto sweep = [&](auto mode_c) {
+                constexpr int MODE = decltype(mode_c)::value;  // 0 general, 1 safe range, 2 safe + expanded form
+                constexpr bool SAFE = MODE >= 1;
                 auto pair_step = [&](int cidx, T (&cacc)[NC]) {
                     T xb[D];
 #pragma unroll
                     for (int tt = 0; tt < D; ++tt) xb[tt] = xc[tt * JC + cidx];
                     const T scol = sc[cidx];
+                    if constexpr (MODE == 2) {
+                        const T nb = nbc[cidx];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const T gcol_row = gc[cidx];
+                            const T gcol = (off0 == 0) ? T(0) : gcol_row;
+                            T u = nb;  // |b|^2 - 2 a.b  (xb holds -2 b)
+#pragma unroll
+                            for (int tt = 0; tt < D; ++tt) u = fma(ar[r][tt], xb[tt], u);
+                            const T kv = exp2neg16(u, tab_s);  // K' / erow; RBF: H = K'
+                            const T hq = kv * (narow[r] + u);
+                            sacc[r] = fma(kv, gcol_row, sacc[r]);
+                            cacc[0] = fma(kv, grow[r], cacc[0]);
+                            l1[r][0] = fma(hq, scol, l1[r][0]);
+                            l2[r][0] = fma(hq, gcol, l2[r][0]);
+                        }
+                        return;
+                    }
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int c = SPREAD ? r : 0;
@@ -451,10 +550,16 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
                 }
             };
             if constexpr (sizeof(T) == 8) {
-                if (safe) sweep(std::true_type{});
-                else sweep(std::false_type{});
+                if constexpr (CAN_EXPAND) {
+                    if (expand) sweep(std::integral_constant<int, 2>{});
+                    else if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                } else {
+                    if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                }
             } else {
-                sweep(std::false_type{});
+                sweep(std::integral_constant<int, 0>{});
             }
             __syncthreads();
 #pragma unroll
@@ -474,9 +579,9 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (valid[r]) atomicAdd(p.sbar + irow[r], sacc[r]);
+        if (valid[r]) atomicAdd(p.sbar + irow[r], sacc[r] * erow[r]);
 #pragma unroll
-        for (int t = 0; t < NLS; ++t) ltot[t] = fma(srow[r], l2[r][t], ltot[t]);
+        for (int t = 0; t < NLS; ++t) ltot[t] = fma(srow[r] * erow[r], l2[r][t], ltot[t]);
     }
 #pragma unroll
     for (int t = 0; t < NLS; ++t) {
