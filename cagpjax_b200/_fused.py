@@ -217,7 +217,9 @@ def sym_forward_peer(family, xs, d, s, k, lengthscale, shard: RowShard, bbox) ->
 def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
     """Returns (A', B', c', Mt, xs): partial statistics over the local rows."""
     d = X.shape[1]
-    xs = N.scale_inputs(family, X, lengthscale, X[0])
+    # origin = centre of the bounding box: stationary kernels only see differences, and centred coordinates keep
+    # |x|^2 small, which is what admits the expanded-distance fast path of the symmetric RBF kernels
+    xs = N.scale_inputs(family, X, lengthscale, 0.5 * (X.amin(dim=0) + X.amax(dim=0)))
     whole = shard.begin == 0 and shard.end == shard.n
     bbox = N.bounding_box(xs) if USE_SYMMETRIC and (whole or shard.block_aligned) else None
     if whole and USE_SYMMETRIC:
