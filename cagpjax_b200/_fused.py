@@ -334,9 +334,10 @@ class KSMatrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X1, X2, lengthscale, s, family, k):
         d = X2.shape[1]
-        xs2 = N.scale_inputs(family, X2, lengthscale, X2[0])
+        origin = 0.5 * (X2.amin(dim=0) + X2.amax(dim=0))  # centred coordinates (see native_local_forward)
+        xs2 = N.scale_inputs(family, X2, lengthscale, origin)
         same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
-        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale, X2[0])
+        xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale, origin)
         Mt = N.ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale, N.union_bounding_box(xs1, xs2))
         ctx.family, ctx.k, ctx.d = family, k, d
         ctx.save_for_backward(xs1, xs2, s, lengthscale)

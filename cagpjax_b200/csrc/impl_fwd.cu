@@ -30,7 +30,7 @@ int fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
             if (gy > 65535) gy = 65535;
             a.blocks_per_cta = (int)((k + gy - 1) / gy);
             gy = (k + a.blocks_per_cta - 1) / a.blocks_per_cta;
-            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
+            const size_t smem = (cagp::FwdCanExpand<T, FAM>::kTabElems + (size_t)JC * cagp::EntrySize<D>::value) * sizeof(T);
             auto kern = cagp::ks_fwd_kernel<T, D, FAM, R, NT, JC>;
             if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<dim3((unsigned)gx, (unsigned)gy), NT, smem, stream>>>(a);

@@ -65,6 +65,13 @@ struct BlockLayout {
     }
 };
 
+// The factored RBF form is compiled into the fp64 RBF instances only (32 KB exp2 table instead of 16 KB).
+template <typename T, int FAM>
+struct FwdCanExpand {
+    static constexpr bool value = sizeof(T) == 8 && FAM == RBF;
+    static constexpr int kTabElems = value ? kExpTab16Elems : ExpTab<T>::kSmemElems;
+};
+
 template <typename T>
 struct FwdArgs {
     const T* xs1; int64_t ld1; int64_t m;
@@ -80,14 +87,24 @@ template <typename T, int D, int FAM, int R, int NT, int JC>
 __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
     constexpr int E = EntrySize<D>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool CAN_EXPAND = FwdCanExpand<T, FAM>::value;
     T* tab = reinterpret_cast<T*>(smem_raw);
-    T* cols = tab + ExpTab<T>::kSmemElems;
+    T* cols = tab + FwdCanExpand<T, FAM>::kTabElems;
     const int tid = threadIdx.x;
-    const unsigned tab_s = ExpTab<T>::load(tab, tid, NT);
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
+    // uniform: fully factored RBF form K' = 2^(-|a|^2) 2^(-|b|^2) 2^(2 a.b) (kernel_math.cuh: launch_is_expandable).
+    // The column factor is folded into the staged weight, the row factor is applied to the finished row sum.
+    const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);
+    unsigned tab_s;
+    if constexpr (CAN_EXPAND) {
+        tab_s = expand ? exptab16_load(tab, tid, NT) : ExpTab<T>::load(tab, tid, NT);
+    } else {
+        tab_s = ExpTab<T>::load(tab, tid, NT);
+    }
+    __syncthreads();  // the table is used by the row set-up and the column staging below
 
     const int64_t row0 = (int64_t)blockIdx.x * (NT * R);
-    T a[R][D];
+    T a[R][D], erow[R];
     int64_t irow[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -95,6 +112,15 @@ __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
         const int64_t ic = irow[r] < p.m ? irow[r] : p.m - 1;
 #pragma unroll
         for (int t = 0; t < D; ++t) a[r][t] = p.xs1[t * p.ld1 + ic];
+        erow[r] = T(1);
+        if constexpr (CAN_EXPAND) {
+            if (expand) {
+                T na = T(0);
+#pragma unroll
+                for (int t = 0; t < D; ++t) na = fma(a[r][t], a[r][t], na);
+                erow[r] = exp2neg16(na, tab_s);
+            }
+        }
     }
     const int b_begin = blockIdx.y * p.blocks_per_cta;
     const int b_end = min(p.lay.k, b_begin + p.blocks_per_cta);
@@ -109,40 +135,63 @@ __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
             __syncthreads();
             for (int idx = tid; idx < cl; idx += NT) {
                 const int64_t j = j0 + c0 + idx;
+                T nb = T(0);
 #pragma unroll
-                for (int t = 0; t < D; ++t) cols[idx * E + t] = p.xs2[t * p.ld2 + j];
-                cols[idx * E + D] = p.s[j];
+                for (int t = 0; t < D; ++t) {
+                    const T v = p.xs2[t * p.ld2 + j];
+                    nb = fma(v, v, nb);
+                    cols[idx * E + t] = expand ? T(-2) * v : v;
+                }
+                T w = p.s[j];
+                if constexpr (CAN_EXPAND) {
+                    if (expand) w *= exp2neg16(nb, tab_s);
+                }
+                cols[idx * E + D] = w;
             }
             __syncthreads();
-            auto sweep = [&](auto safe_c) {
-                constexpr bool SAFE = decltype(safe_c)::value;
+            auto sweep = [&](auto mode_c) {
+                constexpr int MODE = decltype(mode_c)::value;  // 0 general, 1 safe range, 2 safe + factored form
+                constexpr bool SAFE = MODE >= 1;
 #pragma unroll 2
                 for (int j = 0; j < cl; ++j) {
                     T e[E];
                     load_entry_any<E>(cols + j * E, e);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        T q = T(0);
+                        if constexpr (MODE == 2) {
+                            T u = a[r][0] * e[0];  // -2 a.b
 #pragma unroll
-                        for (int t = 0; t < D; ++t) {
-                            const T df = a[r][t] - e[t];
-                            q = fma(df, df, q);
+                            for (int t = 1; t < D; ++t) u = fma(a[r][t], e[t], u);
+                            acc[r] = fma(exp2neg16(u, tab_s), e[D], acc[r]);
+                        } else {
+                            T q = T(0);
+#pragma unroll
+                            for (int t = 0; t < D; ++t) {
+                                const T df = a[r][t] - e[t];
+                                q = fma(df, df, q);
+                            }
+                            const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
+                            acc[r] = fma(kv, e[D], acc[r]);
                         }
-                        const T kv = kernel_value<T, FAM, SAFE>(q, tab_s);
-                        acc[r] = fma(kv, e[D], acc[r]);
                     }
                 }
             };
             if constexpr (sizeof(T) == 8) {
-                if (safe) sweep(std::true_type{});
-                else sweep(std::false_type{});
+                if constexpr (CAN_EXPAND) {
+                    if (expand) sweep(std::integral_constant<int, 2>{});
+                    else if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                } else {
+                    if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                }
             } else {
-                sweep(std::false_type{});
+                sweep(std::integral_constant<int, 0>{});
             }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (irow[r] < p.m) p.Mt[(int64_t)b * p.ldm + irow[r]] = acc[r];
+            if (irow[r] < p.m) p.Mt[(int64_t)b * p.ldm + irow[r]] = acc[r] * erow[r];
     }
 }
 
