@@ -19,6 +19,11 @@ class GaussianDistribution:
         self.solver = solver if solver is not None else Cholesky(1e-6)
         self.batch_shape = ()
         self.event_shape = tuple(loc.shape)
+        self.event_dim = 1
+        self.support = "real_vector"  # numpyro.distributions.constraints.real_vector in the reference
+
+    def shape(self, sample_shape=()):
+        return tuple(sample_shape) + self.batch_shape + self.event_shape
 
     @property
     def mean(self) -> torch.Tensor:

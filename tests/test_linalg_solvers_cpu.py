@@ -500,3 +500,35 @@ def test_pseudo_input_policy_fails_loudly_without_cuda():
     policy = PseudoInputPolicy(torch.zeros(3, 1, dtype=F64), torch.zeros(5, 1, dtype=F64), kernel)
     with pytest.raises(NativeLibraryError):
         policy.to_actions(None)
+
+
+# ------------------------------------------------------------------------------------------------
+# GaussianDistribution (tests/test_distributions.py:17-121 of the reference)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4, 12])
+@pytest.mark.parametrize("dtype", [F32, F64])
+@pytest.mark.parametrize("solver", [Cholesky(1e-6), PseudoInverse()], ids=["cholesky", "pinv"])
+def test_gaussian_distribution_surface(n, dtype, solver):
+    from cagpjax_b200.distributions import GaussianDistribution
+
+    loc = randn(n, seed=1, dtype=dtype)
+    A = randn(n, n, seed=2, dtype=dtype)
+    scale = PSD(Dense(A @ A.T + n * torch.eye(n, dtype=dtype)))
+    dist = GaussianDistribution(loc, scale, solver=solver)
+    assert dist.loc is loc and dist.scale is scale and dist.solver is solver
+    assert dist.batch_shape == () and dist.event_shape == (n,) and dist.event_dim == 1 and dist.shape() == (n,)
+    assert dist.mean.dtype == dtype and torch.allclose(dist.mean, loc)
+    assert dist.variance.shape == (n,) and torch.allclose(dist.variance, torch.diagonal(scale.to_dense()))
+    assert torch.allclose(dist.stddev, torch.sqrt(torch.diagonal(scale.to_dense())))
+    assert dist.covariance() is scale
+    value = randn(n, seed=3, dtype=dtype)
+    lp = dist.log_prob(value)
+    ref = torch.distributions.MultivariateNormal(loc.double(), scale.to_dense().double()).log_prob(value.double())
+    assert lp.dtype == dtype
+    assert torch.allclose(lp.double(), ref, rtol=1e-3 if dtype == F32 else 1e-5)
+    x = dist.sample(7, (20000,))
+    assert x.shape == (20000, n) and x.dtype == dtype
+    assert torch.allclose(x.mean(0), loc, atol=0.15 * float(dist.stddev.max()))
+    emp = torch.cov(x.T.double())
+    assert torch.allclose(emp, scale.to_dense().double(), atol=0.1 * float(scale.to_dense().abs().max()))
+    assert dist.sample(7).shape == (n,)
