@@ -56,8 +56,11 @@ typedef struct cagp_kernel_desc {
   const void* lengthscale;   /* device pointer, n_lengthscale elements */
   const void* bbox;          /* optional (may be NULL): device pointer to the bounding box of ALL scaled points
                                 of the call, {min_0..min_{D-1}, max_0..max_{D-1}} with D = cagp_padded_dim(d)
-                                (cagp_bounding_box).  Lets the symmetric kernels prove that no pair can reach
-                                the exp2 clamp and drop 3 integer instructions per kernel evaluation. */
+                                (cagp_bounding_box).  Lets the kernels prove launch-wide (a) that no pair can reach
+                                the exp2 clamp (3 integer instructions less per evaluation) and (b), for fp64 RBF
+                                with every |x|^2 < 300, that the factored form K' = 2^(-|a|^2) 2^(-|b|^2) 2^(2 a.b)
+                                is accurate (D instead of 2 D fp64 slots per distance); results agree with the
+                                general path to ~3e-14 relative. */
 } cagp_kernel_desc;
 
 const char* cagp_last_error_string(void);
