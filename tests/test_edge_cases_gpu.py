@@ -121,3 +121,50 @@ def test_gaussian_distribution_surface():
         assert samples.shape == (4000, 25)
         assert torch.allclose(samples.mean(0).cpu(), om, atol=0.05)
         assert torch.allclose(samples.var(0).cpu(), ov, rtol=0.2, atol=1e-3)
+
+
+@pytest.mark.parametrize("ls", [0.9, 0.2, 0.17, 0.16, 0.05])
+@pytest.mark.parametrize("n,k,d", [(1500, 3, 3), (700, 64, 2)])
+def test_rbf_range_modes_agree_with_oracle(ls, n, k, d):
+    """The fp64 RBF kernels pick one of three arithmetic forms from the bounding box of the scaled inputs:
+    expanded / factored distance (|x|^2 < 300 everywhere; SINGLE-shape kernels and the rectangular forward),
+    clamp-free exp2 (all q < 990; what the SPREAD-shape kernels of the k = 64 case use), general.  X in [0, 4]^d:
+    the lengthscale moves the same data across the thresholds (d = 3: expanded up to ls = 0.17, general from 0.16);
+    every form must match the oracle, forward and reverse."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64) * 4
+    s = torch.randn(n, generator=g, dtype=torch.float64)
+    Gt = torch.randn(k, n, generator=g, dtype=torch.float64)
+    lst = torch.tensor([ls], dtype=torch.float64)
+    lso = lst.clone().requires_grad_(True)
+    so = s.clone().requires_grad_(True)
+    Ko = O.cross_covariance("rbf", x, x, lso, torch.tensor(1.0, dtype=torch.float64))
+    Mo = Ko @ O.bds_dense(so, k)  # (n, k)
+    gs, gl = torch.autograd.grad((Mo.T * Gt).sum(), [so, lso])
+
+    xd, sd, lsd = x.to(DEV), s.to(DEV), lst.to(DEV)
+    xs = N.scale_inputs("rbf", xd, lsd, 0.5 * (xd.amin(0) + xd.amax(0)))
+    bbox = N.bounding_box(xs)
+    Mt_sym = N.ks_blocksparse_fwd_sym("rbf", xs, d, sd, k, lsd, bbox=bbox)
+    Mt_rect = N.ks_blocksparse_fwd("rbf", xs, xs, d, sd, k, lsd, bbox)
+    assert rel_err(Mt_sym.T, Mo) < 1e-11
+    assert rel_err(Mt_rect.T, Mo) < 1e-11
+    sb, lb = N.ks_blocksparse_bwd_sym("rbf", xs, d, sd, k, Gt.to(DEV), lsd, bbox=bbox)
+    assert rel_err(sb, gs) < 1e-10
+    assert abs(float(lb[0]) - float(gl[0])) <= 1e-10 * max(abs(float(gl[0])), float((Mo.detach().abs().T * Gt.abs()).sum()))
+
+
+def test_expanded_form_falls_back_for_wide_data():
+    """Same data, shifted far from the origin and spread over hundreds of lengthscales: the centred coordinates
+    exceed the |x|^2 < 300 proof, the kernels must take the difference-based forms and stay exact."""
+    n, d, k = 900, 3, 5
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64) * 400 + 1e5  # ~340 scaled units wide
+    x[: n // 2] = x[n // 2:][: n // 2] + 0.3 * torch.randn(n // 2, d, generator=g, dtype=torch.float64)  # near pairs
+    s = torch.randn(n, generator=g, dtype=torch.float64)
+    ls = torch.tensor([1.0], dtype=torch.float64)
+    ref = O.projected_kernel_blocksparse("rbf", x.numpy(), x.numpy(), ls.numpy(), s.numpy(), k)
+    xd = x.to(DEV)
+    xs = N.scale_inputs("rbf", xd, ls.to(DEV), 0.5 * (xd.amin(0) + xd.amax(0)))
+    Mt = N.ks_blocksparse_fwd_sym("rbf", xs, d, s.to(DEV), k, ls.to(DEV), bbox=N.bounding_box(xs))
+    assert rel_err(Mt.T, ref) < 1e-10
