@@ -116,11 +116,15 @@ __device__ __forceinline__ double exp2neg(double u, unsigned tab_s) {
 // 2^(-f) on [-2^-9, 2^-9] (near-minimax, max relative error 1.75e-14, equi-oscillating - against 1.4e-13 for the
 // Taylor cubic); a quartic would reach 4e-17 for one more DFMA per evaluation, which costs 5 % of the kernel for
 // accuracy the 1e-10 parity bar does not need.  fp64 pipe cost: 3 DADD + 3 DFMA + 1 DMUL.
+template <bool I2F = false>
 __device__ __forceinline__ double exp2neg16(double u, unsigned tab_lane) {
     constexpr double kMagic = 26388279066624.0;  // 1.5 * 2^44
     const double t = u + kMagic;
     const unsigned lo = (unsigned)__double2loint(t);
-    const double f = u - (t - kMagic);
+    // I2F: J = round(256 u) sits in the low mantissa word; its conversion runs on the conversion unit instead of the
+    // fp64 pipe and u - J / 256 is exact in one FMA (bit-identical to the two dependent DADDs).  Measured at C3:
+    // symmetric forward 499 -> 489 ms, backward unchanged (633 vs 636 ms), so only the forward enables it.
+    const double f = I2F ? fma(__int2double_rn((int)lo), -0.00390625, u) : u - (t - kMagic);
     unsigned idx, addr;
     asm("and.b32 %0, %1, 255;" : "=r"(idx) : "r"(lo));
     asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(idx), "r"(tab_lane));
@@ -136,6 +140,7 @@ __device__ __forceinline__ double exp2neg16(double u, unsigned tab_lane) {
     asm("mad.lo.s32 %0, %1, -4096, %2;" : "=r"(thi) : "r"(lo), "r"(__double2hiint(tv)));
     return __hiloint2double(thi, __double2loint(tv)) * p;
 }
+template <bool I2F = false>
 __device__ __forceinline__ float exp2neg16(float u, unsigned) { return u; }  // never used (fp64 only)
 
 template <bool SAFE = false>

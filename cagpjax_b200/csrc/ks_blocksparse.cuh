@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
                             T u = a[r][0] * e[0];  // -2 a.b
 #pragma unroll
                             for (int t = 1; t < D; ++t) u = fma(a[r][t], e[t], u);
-                            acc[r] = fma(exp2neg16(u, tab_s), e[D], acc[r]);
+                            acc[r] = fma(exp2neg16<true>(u, tab_s), e[D], acc[r]);
                         } else {
                             T q = T(0);
 #pragma unroll

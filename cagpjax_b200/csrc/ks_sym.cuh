@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                             T u = nb;  // |b|^2 - 2 a.b  (xb holds -2 b)
 #pragma unroll
                             for (int tt = 0; tt < D; ++tt) u = fma(ar[r][tt], xb[tt], u);
-                            const T kv = exp2neg16(u, tab_s);  // K' / 2^(-|a|^2)
+                            const T kv = exp2neg16<true>(u, tab_s);  // K' / 2^(-|a|^2)
                             racc[r] = fma(kv, w, racc[r]);
                             cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
                         }
