@@ -23,6 +23,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -156,6 +157,19 @@ def cpu_port_step_seconds(cfg, n_sample: int, threads: int):
     t0 = time.perf_counter()
     O.elbo_and_grad_literal(cfg["family"], x, y, p, k)
     return time.perf_counter() - t0, k
+
+
+def cpu_structured_pairs_per_sec(cfg, n_sample: int = 12288):
+    """Kernel pairs per second of the oracle's STRUCTURED O(n^2) forward K'S (never densifies S) on the host
+    (lets the algorithmic speed-up - no dense n x k products - be separated from the hardware one)."""
+    from oracle import cagp_oracle as O
+
+    cfg_s = dict(cfg, n=n_sample)
+    k = max(1, min(cfg["k"], n_sample // 8))
+    x, y, s = synth(cfg_s, "cpu", torch.float64)
+    t0 = time.perf_counter()
+    O.projected_kernel_blocksparse(cfg["family"], x.numpy(), x.numpy(), np.ones(1), s.numpy(), k)
+    return n_sample * n_sample / (time.perf_counter() - t0)
 
 
 def run_reference(args, cfg):
@@ -320,7 +334,8 @@ def main():
         dt, k_s = cpu_port_step_seconds(cfg, args.ref_n, threads)
         scale = (n / args.ref_n) ** 2 * (k / k_s)
         cpu_baseline = {"value": 1.0 / (dt * scale), "unit": "steps/s", "cores": threads, "kind": "port",
-                        "sample": f"oracle literal port of the reference path at n={args.ref_n},k={k_s}: {dt:.2f} s/step measured, extrapolated x{scale:.3g} (n^2 k) to the named shape"}
+                        "sample": f"oracle literal port of the reference path at n={args.ref_n},k={k_s}: {dt:.2f} s/step measured, extrapolated x{scale:.3g} (n^2 k) to the named shape",
+                        "structured_fwd_pairs_per_sec": cpu_structured_pairs_per_sec(cfg)}
 
     if rank == 0:
         out = {
