@@ -32,7 +32,7 @@ int dense_fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64
                 if (cudaMemset2DAsync(Y, (size_t)ldy * sizeof(T), 0, (size_t)p * sizeof(T), (size_t)m, stream) != cudaSuccess)
                     return fail(CAGP_ERR_CUDA, "memset Y failed");
             }
-            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)cagp::kDenseJC * (D + cagp::kDenseKsStride + cagp::kDenseVsStride)) * sizeof(T);
+            const size_t smem = (cagp::ExpTab<T>::kSmemElems + (size_t)cagp::kDenseJC * (2 * D + cagp::kDenseKsStride + 2 * cagp::kDenseVsStride)) * sizeof(T);
             auto kern = cagp::ks_dense_fwd_kernel<T, D, FAM>;
             if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), cagp::kDenseThreads, smem, stream>>>(a);

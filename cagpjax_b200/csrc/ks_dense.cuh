@@ -57,16 +57,31 @@ __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
 
+// 8- or 4-byte asynchronous global -> shared copy; !valid writes zeros (src-size 0, the source is not read)
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? (int)sizeof(T) : 0;
+    if constexpr (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Stage pipeline: the V tile and the column coordinates of stage s + 1 travel global -> shared with cp.async
+// while stage s is evaluated (phase A) and contracted (phase B); two barriers per stage.
 template <typename T, int D, int FAM>
 __global__ void __launch_bounds__(kDenseThreads, 2) ks_dense_fwd_kernel(const DenseFwdArgs<T> p) {
     constexpr int JC = kDenseJC, TM = kDenseRows, TP = kDenseCols;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
-    T* xc = tab + ExpTab<T>::kSmemElems;  // [D][JC]
+    T* xc0 = tab + ExpTab<T>::kSmemElems;  // [2][D][JC]
     constexpr int KS = kDenseKsStride, VS = kDenseVsStride;
     constexpr bool kMma = sizeof(T) == 8;  // fp64: tensor-core MMA for the GEMM phase; fp32: FMA register tile
-    T* Ks = xc + D * JC;                  // [JC][KS]
-    T* Vs = Ks + JC * KS;                 // [JC][VS]
+    T* Ks = xc0 + 2 * D * JC;             // [JC][KS]
+    T* Vs0 = Ks + JC * KS;                // [2][JC][VS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = ExpTab<T>::load(tab, tid, kDenseThreads);
     // MMA warp tile: 32 rows x 32 columns (2 x 4 warp grid): 4 x 4 m8n8 accumulator tiles per warp
@@ -90,19 +105,32 @@ __global__ void __launch_bounds__(kDenseThreads, 2) ks_dense_fwd_kernel(const De
     const int colbase = blockIdx.z * TP;
     const int64_t j_begin = (int64_t)blockIdx.y * p.jchunk;
     const int64_t j_end = min(p.n, j_begin + p.jchunk);
-    for (int64_t c0 = j_begin; c0 < j_end; c0 += JC) {
+    auto stage_load = [&](int buf, int64_t c0) {
         const int cl = (int)min((int64_t)JC, j_end - c0);
-        __syncthreads();
+        T* xc = xc0 + buf * (D * JC);
+        T* Vs = Vs0 + buf * (JC * VS);
         for (int idx = tid; idx < D * JC; idx += kDenseThreads) {
             const int t = idx / JC, jj = idx % JC;
-            xc[idx] = jj < cl ? p.xs2[t * p.ld2 + c0 + jj] : T(0);
+            const bool ok = jj < cl;
+            cp_async_elem<T>(xc + idx, p.xs2 + t * p.ld2 + (ok ? c0 + jj : j_begin), ok);
         }
         for (int idx = tid; idx < JC * TP; idx += kDenseThreads) {
             const int jj = idx / TP, cc = idx % TP;
             const int gc = colbase + cc;
-            Vs[jj * VS + cc] = (jj < cl && gc < p.p) ? p.V[(c0 + jj) * p.ldv + gc] : T(0);
+            const bool ok = jj < cl && gc < p.p;
+            cp_async_elem<T>(Vs + jj * VS + cc, p.V + (ok ? (c0 + jj) * p.ldv + gc : 0), ok);
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+    if (j_begin < j_end) stage_load(0, j_begin);
+    int buf = 0;
+    for (int64_t c0 = j_begin; c0 < j_end; c0 += JC, buf ^= 1) {
+        const int cl = (int)min((int64_t)JC, j_end - c0);
+        const T* xc = xc0 + buf * (D * JC);
+        const T* Vs = Vs0 + buf * (JC * VS);
+        cp_async_wait_all();
+        __syncthreads();  // stage data visible; everybody is done with phase B of the previous stage
+        if (c0 + JC < j_end) stage_load(buf ^ 1, c0 + JC);
         // phase A: 64 x 32 kernel tile, 8 values per thread
 #pragma unroll 2
         for (int e = 0; e < JC / 4; ++e) {
