@@ -286,27 +286,46 @@ def _softplus_inv(x):
 
 
 def fit(*, model, objective: Callable, train_data: Dataset, optim="adamw", num_iters: int = 100,
-        learning_rate: float = 0.01, key=None, verbose: bool = False):
+        learning_rate: float = 0.01, key=None, verbose: bool = False, cuda_graph: bool = False):
     """Gradient-based optimisation of ``objective(model, train_data)`` over the trainable leaves.
 
     Mirrors ``gpx.fit(model=, objective=, train_data=, optim=, num_iters=, key=)``: positive
     parameters are optimised in an unconstrained (softplus) space, as GPJax does.  ``optim`` is
     "adamw", "adam", "sgd" or a callable ``params -> torch.optim.Optimizer``.  Returns
     ``(model, history)`` with the per-iteration objective values.
+
+    ``cuda_graph=True`` (single GPU, built-in optimisers): after three eager iterations the whole step - forward
+    kernels, k x k algebra, reverse mode, optimiser update - is captured once in a CUDA graph and replayed.  A step
+    of a small problem (README shape: n = 1000, k = 10) is ~100 launches of microsecond kernels, i.e. bound by
+    launch latency and Python; the replay removes both (what ``jax.jit`` does for the reference's training loop).
     """
     leaves = trainable_leaves(model)
     raw = []
     for owner, attr, leaf in leaves:
         v = unwrap(leaf).detach().clone()
+        if cuda_graph and train_data.X is not None:
+            v = v.to(train_data.X.device)  # every leaf the captured step updates must live on the GPU
         if isinstance(leaf, Parameter) and leaf.positive:
             v = _softplus_inv(v)
         raw.append(v.requires_grad_(True))
+    if cuda_graph and (callable(optim) or not raw or not all(r.is_cuda for r in raw)):
+        raise ValueError("cuda_graph=True needs CUDA training data and one of the built-in optimisers")
+    if cuda_graph and raw[0].dtype == torch.float64 and torch.get_default_dtype() != torch.float64:
+        # capturable Adam keeps its step counter (hence the bias corrections 1 - beta^t) in the DEFAULT dtype;
+        # in float32 that perturbs a float64 trajectory at the 1e-6 level
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+        try:
+            return fit(model=model, objective=objective, train_data=train_data, optim=optim, num_iters=num_iters,
+                       learning_rate=learning_rate, key=key, verbose=verbose, cuda_graph=True)
+        finally:
+            torch.set_default_dtype(prev)
     if callable(optim):
         opt = optim(raw)
     elif optim == "adamw":
-        opt = torch.optim.AdamW(raw, lr=learning_rate, weight_decay=1e-4)
+        opt = torch.optim.AdamW(raw, lr=learning_rate, weight_decay=1e-4, capturable=cuda_graph)
     elif optim == "adam":
-        opt = torch.optim.Adam(raw, lr=learning_rate)
+        opt = torch.optim.Adam(raw, lr=learning_rate, capturable=cuda_graph)
     elif optim == "sgd":
         opt = torch.optim.SGD(raw, lr=learning_rate)
     else:
@@ -322,15 +341,43 @@ def fit(*, model, objective: Callable, train_data: Dataset, optim="adamw", num_i
             else:
                 setattr(owner, attr, v)
 
-    history = []
-    for it in range(num_iters):
-        opt.zero_grad(set_to_none=True)
+    def step():
         install(detach=False)
         loss = objective(model, train_data)
         loss.backward()
         opt.step()
-        history.append(loss.detach())
-        if verbose and (it % 10 == 0 or it == num_iters - 1):
-            print(f"iter {it}: objective {float(loss):.6f}")
+        return loss
+
+    history = []
+    n_eager = min(num_iters, 3) if cuda_graph else num_iters
+    if cuda_graph:  # warm-up on a side stream, as torch.cuda.graph requires
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)  # the leaves were created on the default stream; the mismatch is intended here
+        side = torch.cuda.Stream(device=raw[0].device)
+        side.wait_stream(torch.cuda.current_stream(raw[0].device))
+        ctx = torch.cuda.stream(side)
+    else:
+        import contextlib
+
+        ctx = contextlib.nullcontext()
+    with ctx:
+        for it in range(n_eager):
+            opt.zero_grad(set_to_none=True)
+            loss = step()
+            history.append(loss.detach().clone() if cuda_graph else loss.detach())
+            if verbose and (it % 10 == 0 or it == num_iters - 1):
+                print(f"iter {it}: objective {float(loss):.6f}")
+    if cuda_graph and num_iters > n_eager:
+        torch.cuda.current_stream(raw[0].device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = step()
+        for it in range(n_eager, num_iters):
+            graph.replay()
+            history.append(static_loss.detach().clone())
+            if verbose and (it % 10 == 0 or it == num_iters - 1):
+                print(f"iter {it}: objective {float(static_loss):.6f}")
     install(detach=True)
     return model, torch.stack(history) if history else torch.zeros(0)
