@@ -231,9 +231,16 @@ def _fused_dense_statistics_ok(policy, actions, cov_xx) -> bool:
     from ..operators.annotations import ScaledOrthogonal
     from ..ops import StiefelAnnotation, UnitaryAnnotation
 
-    if cov_xx.process_group is not None or getattr(policy, "fused_statistics", False):
+    orthogonal = any(actions.isa(a) for a in (StiefelAnnotation, UnitaryAnnotation, ScaledOrthogonal))
+    if cov_xx.process_group is not None:
+        if not (orthogonal or getattr(policy, "fused_statistics", False)):
+            import warnings
+
+            warnings.warn("row-sharded run with dense actions that are not orthogonal by construction: the all-reduced "
+                          "k-sized statistics lose accuracy when S^T K S is ill-conditioned; wrap the policy in "
+                          "OrthogonalizationPolicy (as the reference recommends for pseudo-input actions)")
         return True
-    return any(actions.isa(a) for a in (StiefelAnnotation, UnitaryAnnotation, ScaledOrthogonal))
+    return orthogonal or getattr(policy, "fused_statistics", False)
 
 
 def _elbo_fused_dense_impl(model, state):

@@ -268,3 +268,50 @@ def test_fit_with_pseudo_inputs_improves_elbo():
     assert torch.isfinite(history).all()
     assert float(history[-1]) < float(history[0])
     assert not torch.equal(gpx.unwrap(model.policy.base_policy.pseudo_inputs), z0)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures of the widened rows (tests/golden/make_golden_ext.py)
+# ------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from tests.golden.make_golden_ext import CASES as EXT_CASES, HYPER  # noqa: E402
+
+EXT_GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "cagp_golden_ext.npz"))
+
+
+@pytest.mark.parametrize("case", EXT_CASES, ids=[c[0] for c in EXT_CASES])
+def test_cuda_path_reproduces_ext_golden_vectors(case):
+    name, family, n, d, k, policy, solver_name = case
+    G = lambda key: torch.from_numpy(EXT_GOLDEN[f"{name}/{key}"])
+    x, y, z, zt = G("x"), G("y"), G("z"), G("zt")
+    solver = Cholesky(1e-6) if solver_name == "cholesky" else PseudoInverse(grad_rtol=1e-9)
+    to = lambda t: torch.as_tensor(t, dtype=torch.float64).to(DEV)
+    kernel = KERNELS[family](lengthscale=to(0.9), variance=to(HYPER["variance"]),
+                             compute_engine=cagp.computations.LazyKernelComputation())
+    data = gpx.Dataset(to(x), to(y).reshape(-1, 1))
+    if policy == "lanczos":
+        pol = LanczosPolicy(n_actions=k)
+    else:
+        pol = PseudoInputPolicy(gpx.Real(to(z)), data, kernel)
+        if policy == "ortho_qr":
+            pol = OrthogonalizationPolicy(pol, method=OrthogonalizationMethod.QR)
+        elif policy == "ortho_mgs":
+            pol = OrthogonalizationPolicy(pol, method=OrthogonalizationMethod.MGS, n_reortho=1)
+    prior = gpx.Prior(kernel=kernel, mean_function=gpx.Constant(to(HYPER["mean_constant"])))
+    model = cagp.ComputationAwareGP(prior * gpx.Gaussian(n, obs_stddev=to(HYPER["obs_stddev"])), pol, solver)
+    ill = policy == "pseudo"  # raw pseudo-input actions: ill-conditioned k x k systems (see the tests above)
+    vtol, gtol = (1e-6, 1e-4) if ill else (1e-9, 1e-6)
+    with torch.no_grad():
+        st = model.init(data, key=0)
+        q = model.predict(st, to(zt))
+        assert rel_err(model.elbo(st), G("elbo")) < vtol
+        assert rel_err(q.mean, G("mean")) < vtol * 10
+        assert rel_err(q.variance, G("var")) < vtol * 10
+    val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    assert rel_err(-val, G("elbo")) < vtol
+    ograds = {key: G(f"grad_{key}") for key in ("lengthscale", "variance", "obs_stddev", "mean_constant", "pseudo_inputs")}
+    expect = ["lengthscale", "variance", "obs_stddev", "mean_constant"] + ([] if policy == "lanczos" else ["pseudo_inputs"])
+    check_grads(grads, ograds, gtol, expect)
