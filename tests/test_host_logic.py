@@ -39,6 +39,21 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert [lib.cagp_padded_dim(d) for d in (1, 3, 5, 7, 16, 17, 32, 33)] == [1, 3, 8, 8, 16, 32, 32, -1]
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary must be bindable from C / cgo / JNI / XLA FFI: the header compiles as C99 and as C++."""
+    import shutil
+    import subprocess
+
+    header = os.path.join(ROOT, "include", "cagp_b200.h")
+    src_c = tmp_path / "probe.c"
+    src_c.write_text('#include "cagp_b200.h"\nint main(void) { cagp_kernel_desc kd; (void)kd; return (int)sizeof(cagp_status) * 0; }\n'
+                     .replace("sizeof(cagp_status)", "sizeof(enum cagp_status)"))
+    for cc, flags in (("gcc", ["-std=c99", "-pedantic", "-Wall", "-Werror"]), ("g++", ["-std=c++17", "-Wall", "-Werror", "-x", "c++"])):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not available")
+        subprocess.run([cc, *flags, "-fsyntax-only", "-I", os.path.dirname(header), str(src_c)], check=True)
+
+
 def test_no_cpu_fallback_on_kernel_path():
     x = _rand(20, 2)
     kernel = gpx.RBF()
