@@ -214,12 +214,18 @@ def sym_forward_peer(family, xs, d, s, k, lengthscale, shard: RowShard, bbox) ->
 # Local compute (the part that runs native kernels).  Tests for the sharding logic replace this
 # with an oracle-backed callable on CPU (gloo); the product always uses the native one.
 # --------------------------------------------------------------------------------------------
+def _box_centre(X: torch.Tensor) -> torch.Tensor:
+    """Centre of the bounding box of the points (d,), one reduction kernel."""
+    lo, hi = torch.aminmax(X.detach(), dim=0)
+    return torch.lerp(lo, hi, 0.5)
+
+
 def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
     """Returns (A', B', c', Mt, xs): partial statistics over the local rows."""
     d = X.shape[1]
     # origin = centre of the bounding box: stationary kernels only see differences, and centred coordinates keep
     # |x|^2 small, which is what admits the expanded-distance fast path of the symmetric RBF kernels
-    xs = N.scale_inputs(family, X, lengthscale, 0.5 * (X.amin(dim=0) + X.amax(dim=0)))
+    xs = N.scale_inputs(family, X, lengthscale, _box_centre(X))
     whole = shard.begin == 0 and shard.end == shard.n
     bbox = N.bounding_box(xs) if USE_SYMMETRIC and (whole or shard.block_aligned) else None
     if whole and USE_SYMMETRIC:
@@ -334,7 +340,7 @@ class KSMatrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X1, X2, lengthscale, s, family, k):
         d = X2.shape[1]
-        origin = 0.5 * (X2.amin(dim=0) + X2.amax(dim=0))  # centred coordinates (see native_local_forward)
+        origin = _box_centre(X2)  # centred coordinates (see native_local_forward)
         xs2 = N.scale_inputs(family, X2, lengthscale, origin)
         same = X1.data_ptr() == X2.data_ptr() and X1.shape == X2.shape
         xs1 = xs2 if same else N.scale_inputs(family, X1, lengthscale, origin)
