@@ -1,8 +1,11 @@
 """Moore-Penrose pseudo-inverse linear solver (reference: solvers/pseudoinverse.py:17-143).
 
-Works on the k x k projected operators of the CaGP model; the eigendecomposition comes from
-``cagpjax_b200.linalg.eigh`` (dense on the device, or matrix-free Lanczos), so its reverse mode supports
-(almost-)degenerate operators through ``grad_rtol``."""
+Every operation of the solver is a spectral filter: with A = V diag(lam) V^T and a weight vector g(lam),
+``V diag(g) V^T b``.  ``solve`` uses g = 1/lam on the retained eigenvalues, ``unwhiten`` g = sqrt(lam), the
+quadratic forms contract V^T b with g directly.  The eigendecomposition comes from ``cagpjax_b200.linalg.eigh``
+(dense on the device, or matrix-free Lanczos), whose reverse mode tolerates (almost-)degenerate operators through
+``grad_rtol``.  In the CaGP model the operators are the k x k projected covariances, so all of this is k-sized
+device work next to the n^2 kernel passes."""
 
 from __future__ import annotations
 
@@ -16,6 +19,9 @@ from .base import AbstractLinearSolver
 
 
 class PseudoInverseState(NamedTuple):
+    """Spectral data of ``A``: retained-eigenvalue mask, eigenvalues with the discarded ones replaced by 1
+    (``eigvals_safe``) and the filtered reciprocals (``eigvals_inv``, 0 where discarded)."""
+
     A: LinearOperator
     eigh_result: EighResult
     eigvals_mask: torch.Tensor
@@ -23,66 +29,82 @@ class PseudoInverseState(NamedTuple):
     eigvals_inv: torch.Tensor
 
 
+def _filter_spectrum(vals: torch.Tensor, rtol: float):
+    """Keep eigenvalues >= rtol * max |eigenvalue| (no host synchronisation: everything stays a device tensor)."""
+    keep = vals >= rtol * vals.abs().max()
+    one, zero = torch.ones_like(vals), torch.zeros_like(vals)
+    safe = torch.where(keep, vals, one)
+    return keep, safe, torch.where(keep, safe.reciprocal(), zero)
+
+
 class PseudoInverse(AbstractLinearSolver):
-    """Least-squares solution ``x = A^+ b``: exact for non-singular ``A``, well defined for singular ``A``.
+    """Least-squares solution ``x = A^+ b``: exact for non-singular ``A``, well defined for singular ``A``, more
+    stable for almost-singular ``A``.  (If the rank of ``A`` depends on hyper-parameters being optimised the
+    objective is discontinuous there - the pseudo-inverse is.)
 
     Attributes:
-        rtol: eigenvalues below ``rtol * max |eigenvalue|`` are treated as zero (default: eps * n, the
-            ``jax.numpy.linalg.lstsq`` heuristic the reference uses).
-        grad_rtol: cutoff for treating eigenvalues as equal in the reverse mode (None: all distinct).
-        alg: eigendecomposition algorithm passed to ``eigh``.
+        rtol: eigenvalues below ``rtol * max |eigenvalue|`` count as zero; default ``eps(dtype) * n``, the
+            ``lstsq`` heuristic the reference takes from JAX.
+        grad_rtol: cutoff for treating eigenvalues as equal in the reverse mode (None: all distinct - not finite
+            for repeated eigenvalues, e.g. sigma^2 S^T S with orthonormal actions).
+        alg: eigendecomposition algorithm passed to ``eigh`` (default dense ``Eigh``).
     """
 
     def __init__(self, rtol: Optional[float] = None, grad_rtol: Optional[float] = None, alg: Optional[Algorithm] = None):
-        if rtol is not None and rtol < 0:
-            raise ValueError("rtol must be non-negative")
-        if grad_rtol is not None and grad_rtol < 0:
-            raise ValueError("grad_rtol must be non-negative")
-        self.rtol = rtol
-        self.grad_rtol = grad_rtol
-        self.alg = alg if alg is not None else Eigh()
+        for name, value in (("rtol", rtol), ("grad_rtol", grad_rtol)):
+            if value is not None and value < 0:
+                raise ValueError(f"{name} must be non-negative")
+        self.rtol, self.grad_rtol = rtol, grad_rtol
+        self.alg = Eigh() if alg is None else alg
 
+    # -- state -----------------------------------------------------------------------------------
     def init(self, A: LinearOperator) -> PseudoInverseState:
         A = lazify(A)
-        n = A.shape[0]
-        rtol_val = self.rtol if self.rtol is not None else float(torch.finfo(A.dtype).eps) * n
-        result = eigh(A, alg=self.alg, grad_rtol=self.grad_rtol)
-        vals = result.eigenvalues
-        cutoff = rtol_val * torch.max(torch.abs(vals))
-        mask = vals >= cutoff
-        safe = torch.where(mask, vals, torch.ones_like(vals))
-        inv = torch.where(mask, torch.reciprocal(safe), torch.zeros_like(vals))
-        return PseudoInverseState(A, result, mask, safe, inv)
+        rtol = float(torch.finfo(A.dtype).eps) * A.shape[0] if self.rtol is None else self.rtol
+        decomposition = eigh(A, alg=self.alg, grad_rtol=self.grad_rtol)
+        return PseudoInverseState(A, decomposition, *_filter_spectrum(decomposition.eigenvalues, rtol))
+
+    @staticmethod
+    def _filtered(state: PseudoInverseState, weights: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """V diag(weights) V^T b for a vector or a matrix b."""
+        V = state.eigh_result.eigenvectors
+        cols = b[:, None] if b.dim() == 1 else b
+        out = V @ (weights[:, None] * (V.T @ cols))
+        return out[:, 0] if b.dim() == 1 else out
+
+    # -- solver interface ------------------------------------------------------------------------
+    def solve(self, state: PseudoInverseState, b: torch.Tensor) -> torch.Tensor:
+        return self._filtered(state, state.eigvals_inv, b)
 
     def unwhiten(self, state: PseudoInverseState, z: torch.Tensor) -> torch.Tensor:
-        sqrt = torch.where(state.eigvals_mask, torch.sqrt(state.eigvals_safe), torch.zeros_like(state.eigvals_safe))
-        x = sqrt[:, None] * z if z.dim() == 2 else sqrt * z
-        return state.eigh_result.eigenvectors @ x
-
-    def solve(self, state: PseudoInverseState, b: torch.Tensor) -> torch.Tensor:
-        vec = b.dim() == 1
-        bm = b[:, None] if vec else b
-        V = state.eigh_result.eigenvectors
-        x = V @ ((V.T @ bm) * state.eigvals_inv[:, None])
-        return x[:, 0] if vec else x
+        """V diag(sqrt(lam)) z: maps IID standard normal z to a sample with covariance A."""
+        root = torch.where(state.eigvals_mask, state.eigvals_safe.sqrt(), torch.zeros_like(state.eigvals_safe))
+        scaled = root[:, None] * z if z.dim() == 2 else root * z
+        return state.eigh_result.eigenvectors @ scaled
 
     def logdet(self, state: PseudoInverseState) -> torch.Tensor:
-        return torch.sum(torch.log(state.eigvals_safe))
+        """Pseudo-determinant: sum of the logs of the retained eigenvalues."""
+        return state.eigvals_safe.log().sum()
 
     def inv_quad(self, state: PseudoInverseState, b: torch.Tensor) -> torch.Tensor:
-        z = state.eigh_result.eigenvectors.T @ b
-        return torch.dot(torch.square(z).reshape(-1), state.eigvals_inv).squeeze()
+        coords = (state.eigh_result.eigenvectors.T @ b).reshape(-1)
+        return torch.dot(coords * coords, state.eigvals_inv)
 
     def inv_congruence_transform(self, state: PseudoInverseState, B):
-        z = state.eigh_result.eigenvectors.T @ B
-        if isinstance(z, LinearOperator):
-            return z.T @ Diagonal(state.eigvals_inv) @ z
-        return z.T @ (state.eigvals_inv[:, None] * z)
+        """``B^T A^+ B``; lazy if ``B`` is an operator, dense otherwise."""
+        coords = state.eigh_result.eigenvectors.T @ B
+        if isinstance(coords, LinearOperator):
+            return coords.T @ Diagonal(state.eigvals_inv) @ coords
+        return coords.T @ (state.eigvals_inv[:, None] * coords)
 
     def trace_solve(self, state: PseudoInverseState, state_other: PseudoInverseState) -> torch.Tensor:
+        """``trace(A^+ B)`` with ``B`` the operator behind ``state_other``."""
         V = state.eigh_result.eigenvectors.to_dense()
-        if isinstance(state_other.eigh_result.eigenvectors, Dense):
-            # tr(V diag(inv) V^T A_other)
-            return torch.einsum("ij,j,kj,ik->", V, state.eigvals_inv, V, state_other.A.to_dense())
-        W = state_other.eigh_result.eigenvectors.T @ V
-        return torch.einsum("ij,j,ij,i->", W, state.eigvals_inv, W, state_other.eigvals_safe)
+        other_vecs = state_other.eigh_result.eigenvectors
+        if isinstance(other_vecs, Dense):
+            # trace(V diag(inv) V^T B) = sum_j inv_j v_j^T B v_j
+            BV = state_other.A.to_dense() @ V
+            return torch.sum(state.eigvals_inv * torch.sum(V * BV, dim=0))
+        # structured B (diagonal-like: its eigenvectors are the identity): sum_ij W_ij^2 inv_j mu_i
+        W = other_vecs.T @ V
+        return torch.sum((W * W) * state.eigvals_inv[None, :] * state_other.eigvals_safe[:, None])
