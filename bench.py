@@ -48,7 +48,11 @@ def pair_flops(family: str, d: int, backward: bool) -> int:
     return base + (6 if backward else 0)
 
 
-FP64_PEAK_TFLOPS = 33.9  # measured DFMA stream on this pool's B200 (profiles/r01_fp64_peaks.json); nominal 37.2
+# Measured fp64 issue rate on this pool's B200 (tools/fp64_ops.cu, profiles/r01_issue_model.txt): DADD, DMUL and
+# DADD/DMUL + DFMA mixes - what the pair kernels execute - issue at 18.56 T lane-instructions/s = 37.1 TFLOP/s
+# FMA-equivalent (nominal 148 x 64 x 2 x 1.965 GHz = 37.2); a pure DFMA stream settles at 34.2.  MEASURED_PEAKS.json
+# has no fp64 entry, so this measured number is the denominator (the stricter of the two).
+FP64_PEAK_TFLOPS = 37.1
 
 # fp64 issue slots actually executed per ORDERED pair by each pair kernel (counted in the SASS of the
 # d = 3 RBF instances; the symmetric kernels evaluate each unordered pair once = half per ordered pair, and
@@ -294,7 +298,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from an ncu
                 # capture of this command at N = 1 (profiles/r01_traffic_c3_sym.csv); algorithmic: G' = 8 n k bytes
                 "traffic": 8.84e9 if (args.config == "c3" and world == 1 and dom == "cagp_ks_blocksparse_bwd_sym") else None,
-                "note": "achieved = declared algorithmic flops (libm-exp cost model, SURVEY 8d: 3d+34 fwd / 3d+40 bwd per ordered pair) / CUDA-event kernel time; peak = measured DFMA stream (of measured; nominal 37.2). frac > 1 because the kernels spend fewer fp64 slots than the declared model (table-based exp2, symmetric tiles); fp64_pipe_frac = executed fp64 slots x 2 / time / peak is the pipe utilisation",
+                "note": "achieved = declared algorithmic flops (libm-exp cost model, SURVEY 8d: 3d+34 fwd / 3d+40 bwd per ordered pair) / CUDA-event kernel time; peak = measured fp64 issue rate of this pool's B200 (37.1 TFLOP/s FMA-equivalent for the DADD/DMUL/DFMA mix; pure DFMA 34.2; nominal 37.2). frac > 1 because the kernels spend fewer fp64 slots than the declared model (table-based exp2, symmetric tiles); fp64_pipe_frac = executed fp64 slots x 2 / time / peak is the pipe utilisation",
                 "pairs_per_sec": pairs_per_launch / (kern_ms[dom] * 1e-3),
                 "fp64_pipe_frac": (pairs_per_launch / (kern_ms[dom] * 1e-3)) * FP64_SLOTS_PER_PAIR.get(dom, 0.0) * 2.0 / 1e12 / FP64_PEAK_TFLOPS
                 if (fam == "rbf" and dd == 3 and cfg["dtype"] == "f64") else None,
