@@ -75,3 +75,41 @@ def test_lanczos_full_run_recovers_the_spectrum():
     vals, vecs = E.lanczos_eigh(A, 15, torch.randn(15, generator=g, dtype=torch.float64))
     assert torch.allclose(vals, torch.linalg.eigvalsh(A), rtol=1e-10)
     assert torch.allclose(vecs @ torch.diag(vals) @ vecs.T, A, atol=1e-9)
+
+
+@pytest.mark.parametrize("policy,solver", [("pseudo", "cholesky"), ("ortho_qr", "cholesky"), ("lanczos", "pinv")])
+def test_ext_oracle_gradients_match_finite_differences(policy, solver):
+    """The golden gradients come from torch reverse mode through the restated chain; central differences on the
+    same chain are the independent check (every leaf, including the pseudo-inputs)."""
+    from tests.golden.make_golden_ext import HYPER, actions_for, make_inputs
+
+    family, n, d, k = "rbf", 60, 2, 5
+    x, y, z, _ = make_inputs(n, d, k)
+    base = dict(lengthscale=torch.tensor(0.9, dtype=torch.float64), variance=torch.tensor(HYPER["variance"], dtype=torch.float64),
+                obs_stddev=torch.tensor(0.3, dtype=torch.float64), mean_constant=torch.tensor(0.5, dtype=torch.float64),
+                pseudo_inputs=z.clone())
+    kw = dict(solver="cholesky", jitter=1e-6) if solver == "cholesky" else dict(solver="pinv")
+
+    def f(leaves):
+        S = actions_for(policy, family, x, leaves["pseudo_inputs"], leaves["lengthscale"], leaves["variance"],
+                        leaves["obs_stddev"], k)
+        return E.elbo_dense_actions(family, x, y, leaves["lengthscale"], leaves["variance"], leaves["obs_stddev"],
+                                    leaves["mean_constant"], S, **kw)[0]
+
+    q = {name: t.clone().requires_grad_(True) for name, t in base.items()}
+    grads = torch.autograd.grad(f(q), list(q.values()), allow_unused=True)
+    for (name, t), g in zip(base.items(), grads):
+        if g is None:  # Lanczos actions do not depend on the pseudo-inputs
+            assert policy == "lanczos" and name == "pseudo_inputs"
+            continue
+        flat = t.reshape(-1)
+        for idx in range(min(flat.numel(), 3)):
+            h = 1e-6 * max(1.0, abs(float(flat[idx])))
+            vals = []
+            for sign in (+1, -1):
+                pert = {kname: v.clone() for kname, v in base.items()}
+                pert[name].reshape(-1)[idx] += sign * h
+                vals.append(float(f(pert)))
+            fd = (vals[0] - vals[1]) / (2 * h)
+            got = float(g.reshape(-1)[idx])
+            assert abs(fd - got) <= 2e-5 * max(1.0, abs(got)), (name, idx, fd, got)
