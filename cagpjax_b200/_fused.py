@@ -473,13 +473,16 @@ class DenseProjectStats(torch.autograd.Function):
     one all-reduce of [S_bar | yt_bar | ls_bar]."""
 
     @staticmethod
-    def forward(ctx, X, lengthscale, S, yt, family, shard, holder):
+    def forward(ctx, X, lengthscale, S, yt, family, shard, holder, kernels=None):
+        # ``kernels``: object providing scale_inputs / ks_dense_fwd / ks_dense_bwd_ls; the product always uses the
+        # native module, the gloo tests of the sharding logic inject an oracle-backed stand-in (no GPU there)
+        KN = N if kernels is None else kernels
         d = X.shape[1]
-        xs = N.scale_inputs(family, X, lengthscale, X[0])
+        xs = KN.scale_inputs(family, X, lengthscale, X[0])
         whole = shard.begin == 0 and shard.end == shard.n
         xs1 = xs if whole else xs[:, shard.begin:shard.end].contiguous()
         Sc = S.contiguous()
-        M = N.ks_dense_fwd(family, xs1, xs, d, Sc, lengthscale)  # (m_local, k)
+        M = KN.ks_dense_fwd(family, xs1, xs, d, Sc, lengthscale)  # (m_local, k)
         Sl, yl = Sc[shard.begin:shard.end], yt[shard.begin:shard.end]
         A, B, c = Sl.T @ M, M.T @ M, M.T @ yl
         if shard.sharded:
@@ -488,7 +491,7 @@ class DenseProjectStats(torch.autograd.Function):
             _all_reduce_sum(packed, shard.group)
             kk = k * k
             A, B, c = packed[:kk].view(k, k), packed[kk:2 * kk].view(k, k), packed[2 * kk:]
-        ctx.family, ctx.d, ctx.shard = family, d, shard
+        ctx.family, ctx.d, ctx.shard, ctx.kernels = family, d, shard, KN
         ctx.save_for_backward(xs, xs1, Sc, M, yt, lengthscale)
         if holder is not None:
             holder["M"] = M
@@ -497,11 +500,11 @@ class DenseProjectStats(torch.autograd.Function):
     @staticmethod
     def backward(ctx, Abar, Bbar, cbar):
         xs, xs1, S, M, yt, lengthscale = ctx.saved_tensors
-        shard = ctx.shard
+        shard, KN = ctx.shard, ctx.kernels
         Sl, yl = S[shard.begin:shard.end], yt[shard.begin:shard.end]
         Mbar = (Sl @ Abar + M @ (Bbar + Bbar.T) + torch.outer(yl, cbar)).contiguous()
-        S_bar = N.ks_dense_fwd(ctx.family, xs, xs1, ctx.d, Mbar, lengthscale)  # K'(X, X_local) Mbar, (n, k)
-        ls_bar = N.ks_dense_bwd_ls(ctx.family, xs1, xs, ctx.d, S, Mbar, lengthscale)
+        S_bar = KN.ks_dense_fwd(ctx.family, xs, xs1, ctx.d, Mbar, lengthscale)  # K'(X, X_local) Mbar, (n, k)
+        ls_bar = KN.ks_dense_bwd_ls(ctx.family, xs1, xs, ctx.d, S, Mbar, lengthscale)
         S_bar[shard.begin:shard.end] += M @ Abar.T
         yt_bar = torch.zeros_like(yt)
         yt_bar[shard.begin:shard.end] = M @ cbar
@@ -510,9 +513,9 @@ class DenseProjectStats(torch.autograd.Function):
             packed = torch.cat([S_bar.reshape(-1), yt_bar, ls_bar.reshape(-1)])
             _all_reduce_sum(packed, shard.group)
             S_bar, yt_bar, ls_bar = packed[:n * k].view(n, k), packed[n * k:n * k + n], packed[n * k + n:]
-        return None, ls_bar.reshape(lengthscale.shape), S_bar, yt_bar, None, None, None
+        return None, ls_bar.reshape(lengthscale.shape), S_bar, yt_bar, None, None, None, None
 
 
-def dense_project_stats(family: str, X, lengthscale, S, yt, shard: Optional[RowShard] = None, holder=None):
+def dense_project_stats(family: str, X, lengthscale, S, yt, shard: Optional[RowShard] = None, holder=None, kernels=None):
     shard = shard or RowShard.full(X.shape[0])
-    return DenseProjectStats.apply(X, lengthscale, S, yt, family, shard, holder)
+    return DenseProjectStats.apply(X, lengthscale, S, yt, family, shard, holder, kernels)
