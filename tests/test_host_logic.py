@@ -269,3 +269,29 @@ def test_closed_form_elbo_matches_autograd_and_oracle(k, n):
         if a.dim() == 2:
             a, b = (a + a.T) / 2, (b + b.T) / 2
         assert torch.allclose(a, b, rtol=1e-10, atol=1e-12 * float(a.abs().max()))
+
+
+def test_bench_contract_on_cpu():
+    """bench.py: the reference arm runs on the host and prints ONE JSON line with the contract's keys; the product
+    arm refuses to run without a CUDA device (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-n", "256"], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    lines = [ln for ln in ref.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in out, key
+    assert out["impl"] == "reference" and out["metric"] == "elbo_grad_steps_per_sec" and out["unit"] == "steps/s"
+    assert out["higher_is_better"] is True and out["vs_baseline"] is None and "workload" in out["config"]
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1 and out["cpu_baseline"]["sample"]
+    assert out["e2e"] == {"value": out["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not torch.cuda.is_available():
+        prod = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                              capture_output=True, text=True, cwd=ROOT, timeout=300)
+        assert prod.returncode != 0 and "no CPU fallback" in (prod.stderr + prod.stdout)
