@@ -328,10 +328,22 @@ class ProjectStats(torch.autograd.Function):
         return None, ls_bar.reshape(lengthscale.shape), s_bar, yt_bar, None, None, None, None, None, None
 
 
+def _like(t: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """``t`` in X's dtype on X's device, contiguous.  The kernels compute in the dtype of the inputs X (the reference
+    relies on JAX type promotion; here every operand of a native call is cast explicitly - a differentiable no-op
+    when it already matches).  Library defaults (gpx.Constant, BlockSparsePolicy.from_random) are float64, so
+    float32 data with default hyper-parameters reaches this cast."""
+    if t.dtype != X.dtype or t.device != X.device:
+        t = t.to(device=X.device, dtype=X.dtype)
+    return t.contiguous()
+
+
 def project_stats(family: str, X, lengthscale, s, yt, k: int, shard: Optional[RowShard] = None, holder=None,
                   local_fwd: Optional[Callable] = None, local_bwd: Optional[Callable] = None):
     shard = shard or RowShard.full(X.shape[0])
-    return ProjectStats.apply(X, lengthscale, s, yt, family, k, shard, holder, local_fwd, local_bwd)
+    X = X.contiguous()
+    return ProjectStats.apply(X, _like(lengthscale, X), _like(s, X), _like(yt, X), family, k, shard, holder,
+                              local_fwd, local_bwd)
 
 
 class KSMatrix(torch.autograd.Function):
@@ -357,7 +369,9 @@ class KSMatrix(torch.autograd.Function):
 
 
 def ks_matrix(family: str, X1, X2, lengthscale, s, k: int) -> torch.Tensor:
-    return KSMatrix.apply(X1, X2, lengthscale, s, family, k)
+    X2 = X2.contiguous()
+    X1 = X2 if X1 is X2 else _like(X1, X2)
+    return KSMatrix.apply(X1, X2, _like(lengthscale, X2), _like(s, X2), family, k)
 
 
 # --------------------------------------------------------------------------------------------
@@ -442,7 +456,8 @@ class CrossCovariance(torch.autograd.Function):
 
 def cross_covariance(family: str, X1, X2, lengthscale) -> torch.Tensor:
     """Materialised unit-variance K'(X1, X2) (m, n) on the device."""
-    return CrossCovariance.apply(X1.contiguous(), X2.contiguous(), lengthscale, family)
+    X1 = X1.contiguous()
+    return CrossCovariance.apply(X1, _like(X2, X1), _like(lengthscale, X1), family)
 
 
 # Below this many columns a dense operand is cheaper as p one-block block-sparse passes (the pair
@@ -453,6 +468,9 @@ DENSE_MIN_COLUMNS = 12
 
 def kernel_matmat(family: str, X1, X2, lengthscale, V: torch.Tensor) -> torch.Tensor:
     """K'(X1, X2) @ V for dense V (n, p), differentiable w.r.t. lengthscale and V."""
+    X2 = X2.contiguous()
+    X1 = X2 if X1 is X2 else _like(X1, X2)
+    lengthscale, V = _like(lengthscale, X2), (V if V.dtype == X2.dtype and V.device == X2.device else V.to(device=X2.device, dtype=X2.dtype))
     if V.shape[1] < DENSE_MIN_COLUMNS:
         # every column of V is a one-block BlockDiagonalSparse (k = 1)
         cols = [ks_matrix(family, X1, X2, lengthscale, V[:, c].contiguous(), 1)[0] for c in range(V.shape[1])]
@@ -518,4 +536,5 @@ class DenseProjectStats(torch.autograd.Function):
 
 def dense_project_stats(family: str, X, lengthscale, S, yt, shard: Optional[RowShard] = None, holder=None, kernels=None):
     shard = shard or RowShard.full(X.shape[0])
-    return DenseProjectStats.apply(X, lengthscale, S, yt, family, shard, holder, kernels)
+    X = X.contiguous()
+    return DenseProjectStats.apply(X, _like(lengthscale, X), _like(S, X), _like(yt, X), family, shard, holder, kernels)

@@ -167,6 +167,10 @@ def _ptr(t: torch.Tensor):
 
 
 def _require_cuda(*tensors: torch.Tensor):
+    """Every tensor handed to one C call must be a contiguous CUDA tensor of ONE dtype on ONE device: the kernel
+    instantiation is picked from the first tensor's dtype and the C ABI sees plain pointers, so a float64 buffer
+    read as float32 (or the reverse, an out-of-bounds read) would be silent.  Callers cast first (see _fused)."""
+    first = None
     for t in tensors:
         if not t.is_cuda:
             raise NativeLibraryError(
@@ -175,6 +179,12 @@ def _require_cuda(*tensors: torch.Tensor):
             )
         if not t.is_contiguous():
             raise ValueError("native kernels need contiguous tensors")
+        if first is None:
+            first = t
+        elif t.dtype != first.dtype or t.device != first.device:
+            raise NativeLibraryError(
+                f"native kernels need all operands in one dtype on one device; got {first.dtype} on {first.device} "
+                f"and {t.dtype} on {t.device}")
 
 
 def _stream(t: torch.Tensor):
@@ -183,6 +193,8 @@ def _stream(t: torch.Tensor):
 
 def make_desc(family: str, lengthscale: torch.Tensor, dtype: torch.dtype, bbox: torch.Tensor = None) -> KernelDesc:
     ls = lengthscale.reshape(-1)
+    if ls.dtype != dtype or not ls.is_cuda or (bbox is not None and (bbox.dtype != dtype or not bbox.is_cuda)):
+        raise NativeLibraryError(f"kernel descriptor: lengthscale / bbox must be CUDA tensors of dtype {dtype}")
     return KernelDesc(FAMILIES[family], dtype_code(dtype), ls.numel(), 0, ls.data_ptr(),
                       bbox.data_ptr() if bbox is not None else None)
 
@@ -207,12 +219,13 @@ def padded_dim(d: int) -> int:
 
 def scale_inputs(family: str, X: torch.Tensor, lengthscale: torch.Tensor, origin: torch.Tensor = None) -> torch.Tensor:
     """xs (padded_dim(d), n): inputs shifted by ``origin`` (d,), scaled and transposed."""
-    _require_cuda(X, lengthscale)
     n, d = X.shape
+    ls = lengthscale.reshape(-1).to(device=X.device, dtype=X.dtype).contiguous()
     if origin is not None:
-        origin = origin.detach().reshape(-1).to(X.dtype).contiguous()
-        _require_cuda(origin)
-    ls = lengthscale.reshape(-1).to(X.dtype).contiguous()
+        origin = origin.detach().reshape(-1).to(device=X.device, dtype=X.dtype).contiguous()
+        _require_cuda(X, ls, origin)
+    else:
+        _require_cuda(X, ls)
     xs = torch.empty((padded_dim(d), n), dtype=X.dtype, device=X.device)
     kd = make_desc(family, ls, X.dtype)
     with torch.cuda.device(X.device), _timed("cagp_scale_inputs", X, 0):
@@ -226,7 +239,7 @@ def ks_blocksparse_fwd(family, xs1, xs2, d, s, k, lengthscale, bbox=None) -> tor
     _require_cuda(xs1, xs2, s)
     m, n = xs1.shape[1], xs2.shape[1]
     Mt = torch.empty((k, m), dtype=xs1.dtype, device=xs1.device)
-    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs1.device, dtype=xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype, bbox)
     with torch.cuda.device(xs1.device), _timed("cagp_ks_blocksparse_fwd", xs1, m * n):
         _check(load().cagp_ks_blocksparse_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(s), k, _ptr(Mt), m,
@@ -238,7 +251,7 @@ def ks_blocksparse_bwd(family, xs1, xs2, d, s, k, Gt, lengthscale):
     """(s_bar (n), ls_bar (n_lengthscale)) for cotangent Gt (k, m)."""
     _require_cuda(xs1, xs2, s, Gt)
     m, n = xs1.shape[1], xs2.shape[1]
-    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs1.device, dtype=xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype)
     lib = load()
     ws_bytes = lib.cagp_ks_bwd_ws_bytes(byref(kd), m, n, d, k)
@@ -259,7 +272,7 @@ def ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, a_begin=0, a_end=No
     a_end = k if a_end is None else a_end
     full = a_begin == 0 and a_end == k
     Mt = out if out is not None else (torch.empty if full else torch.zeros)((k, n), dtype=xs.dtype, device=xs.device)
-    ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs.device, dtype=xs.dtype).contiguous()
     kd = make_desc(family, ls, xs.dtype, bbox)
     with torch.cuda.device(xs.device), _timed("cagp_ks_blocksparse_fwd_sym", xs, n * n * (a_end - a_begin) // k):
         _check(load().cagp_ks_blocksparse_fwd_sym(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, _ptr(Mt), n,
@@ -273,7 +286,7 @@ def ks_blocksparse_fwd_sym_peer(family, xs, d, s, k, lengthscale, a_begin, a_end
     _require_cuda(xs, s)
     n = xs.shape[1]
     world = len(panel_ptrs)
-    ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs.device, dtype=xs.dtype).contiguous()
     kd = make_desc(family, ls, xs.dtype, bbox)
     ptrs = (c_void_p * world)(*[c_void_p(int(p)) for p in panel_ptrs])
     rb = (c_int64 * (world + 1))(*[int(v) for v in row_begin])
@@ -287,7 +300,7 @@ def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_en
     _require_cuda(xs, s, Gt)
     n = xs.shape[1]
     a_end = k if a_end is None else a_end
-    ls = lengthscale.reshape(-1).to(xs.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs.device, dtype=xs.dtype).contiguous()
     kd = make_desc(family, ls, xs.dtype, bbox)
     lib = load()
     ws_bytes = lib.cagp_ks_bwd_sym_ws_bytes(byref(kd), n, d, k, a_begin, a_end)
@@ -306,7 +319,7 @@ def ks_dense_fwd(family, xs1, xs2, d, V, lengthscale) -> torch.Tensor:
     _require_cuda(xs1, xs2, V)
     m, n, p = xs1.shape[1], xs2.shape[1], V.shape[1]
     Y = torch.empty((m, p), dtype=xs1.dtype, device=xs1.device)
-    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs1.device, dtype=xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype)
     with torch.cuda.device(xs1.device), _timed("cagp_ks_dense_fwd", xs1, m * n):
         _check(load().cagp_ks_dense_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(V), p, p, _ptr(Y), p,
@@ -318,7 +331,7 @@ def ks_dense_bwd_ls(family, xs1, xs2, d, V, Ybar, lengthscale) -> torch.Tensor:
     """ls_bar (n_lengthscale) = sum_ij (Ybar_i . V_j) dK'_ij / d lengthscale."""
     _require_cuda(xs1, xs2, V, Ybar)
     m, n, p = xs1.shape[1], xs2.shape[1], V.shape[1]
-    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs1.device, dtype=xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype)
     lib = load()
     ws_bytes = lib.cagp_ks_dense_bwd_ls_ws_bytes(byref(kd), m, n, d)
@@ -336,7 +349,7 @@ def cross_cov_fwd(family, xs1, xs2, d, lengthscale) -> torch.Tensor:
     _require_cuda(xs1, xs2)
     m, n = xs1.shape[1], xs2.shape[1]
     C = torch.empty((m, n), dtype=xs1.dtype, device=xs1.device)
-    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs1.device, dtype=xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype)
     with torch.cuda.device(xs1.device), _timed("cagp_cross_cov_fwd", xs1, m * n):
         _check(load().cagp_cross_cov_fwd(byref(kd), _ptr(xs1), m, m, _ptr(xs2), n, n, d, _ptr(C), n, _stream(xs1)),
@@ -349,7 +362,7 @@ def cross_cov_bwd(family, xs1, xs2, d, Cbar, lengthscale):
     Cbar = Cbar.contiguous()
     _require_cuda(xs1, xs2, Cbar)
     m, n = xs1.shape[1], xs2.shape[1]
-    ls = lengthscale.reshape(-1).to(xs1.dtype).contiguous()
+    ls = lengthscale.reshape(-1).to(device=xs1.device, dtype=xs1.dtype).contiguous()
     kd = make_desc(family, ls, xs1.dtype)
     lib = load()
     ws_bytes = lib.cagp_cross_cov_bwd_ws_bytes(byref(kd), m, n, d)

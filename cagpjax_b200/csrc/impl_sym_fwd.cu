@@ -25,15 +25,29 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                 const int64_t own_rows = row_begin[me + 1] - row_begin[me];
                 a.til = make_sym_tiling(n, k, a_begin, a_end, sh);
                 a.bbox = (const T*)kd->bbox;
+                a.defer_expandable = 0;
                 const int64_t gx = sym_grid_x(a.til);
                 if (gx < 1) return (int)CAGP_OK;
                 const int gy = sym_choose_groups(a.til, gx);
+                // fast path (ks_symx.cuh): both kernels are launched, the bounding box decides on the device which
+                // of the two does the work (the other returns at once) - no host synchronisation
+                bool fast = false;
+                int tiles_main = a.til.tiles_main, tiles_last = a.til.tiles_last;
+                if constexpr (std::is_same<T, double>::value && FAM == cagp::RBF && D <= 4) {
+                    fast = !sh.spread && symx_applicable(kd, n, k, dp, false);
+                    if (fast) {
+                        const cagp::SymTiling tf = make_sym_tiling(n, k, a_begin, a_end, symx_shape(false));
+                        tiles_main = tf.tiles_main > tiles_main ? tf.tiles_main : tiles_main;
+                        tiles_last = tf.tiles_last > tiles_last ? tf.tiles_last : tiles_last;
+                        a.defer_expandable = 1;
+                    }
+                }
                 // column sums of a block that is split over several CTAs are accumulated atomically
                 // (single device only; in peer mode the caller zeroes the panels before the cross-rank barrier)
                 if (world == 1) {
-                    if (a.til.tiles_main > 1) {
+                    if (tiles_main > 1) {
                         if (cudaMemsetAsync(Mt, 0, (size_t)k * ldm * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
-                    } else if (a.til.tiles_last > 1) {
+                    } else if (tiles_last > 1) {
                         if (cudaMemsetAsync((T*)Mt + (size_t)(k - 1) * ldm, 0, (size_t)own_rows * sizeof(T), stream) != cudaSuccess) return fail(CAGP_ERR_CUDA, "memset Mt failed");
                     }
                 }
@@ -50,7 +64,11 @@ int sym_fwd_impl(const cagp_kernel_desc* kd, const void* xs, int64_t n, int64_t 
                     if constexpr (R >= 2) return launch(std::true_type{});
                     else return fail(CAGP_ERR_UNSUPPORTED, "spread shape needs R >= 2");
                 }
-                return launch(std::false_type{});
+                if (int rc2 = launch(std::false_type{})) return rc2;
+                if constexpr (std::is_same<T, double>::value && FAM == cagp::RBF && D <= 4) {
+                    if (fast) return symx_fwd_launch_any<T>(dp, a, n, k, a_begin, a_end, stream);
+                }
+                return (int)CAGP_OK;
             });
         });
     });

@@ -102,6 +102,7 @@ struct SymFwdArgs {
     int world, me;
     const T* bbox;  // bounding box of the scaled inputs (2 * D values) or null
     SymTiling til;
+    int defer_expandable;  // 1: return at once when the expanded form applies (ks_symx.cuh computes the launch)
 };
 
 template <typename T>
@@ -113,6 +114,7 @@ struct SymBwdArgs {
     T* ls_part;  // [gridDim.y * gridDim.x][NLS]
     const T* bbox;  // bounding box of the scaled inputs (2 * D values) or null
     SymTiling til;
+    int defer_expandable;  // see SymFwdArgs
 };
 
 // Row placement of a CTA.  SINGLE: all R rows in block a0 (a_of(r) == a0).  SPREAD: row r in block a0 + r.
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     // uniform: expanded distance form with the replicated exp2 table (kernel_math.cuh)
     const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);
+    if (p.defer_expandable && expand) return;  // uniform: the fast-path kernel (ks_symx.cuh) does this launch
     unsigned tab_s;
     if constexpr (CAN_EXPAND) {
         tab_s = expand ? exptab16_load(tab, tid, nthreads) : ExpTab<T>::load(tab, tid, nthreads);
@@ -368,6 +371,7 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);  // uniform, see the forward kernel
+    if (p.defer_expandable && expand) return;  // uniform: the fast-path kernel (ks_symx.cuh) does this launch
     unsigned tab_s;
     if constexpr (CAN_EXPAND) {
         tab_s = expand ? exptab16_load(tab, tid, nthreads) : ExpTab<T>::load(tab, tid, nthreads);

@@ -57,4 +57,27 @@ inline int sym_choose_groups(cagp::SymTiling& t, int64_t gx) {
     return (n_off0 + t.offs_per_cta - 1) / t.offs_per_cta;
 }
 
+// ---- fast path (ks_symx.cuh, impl_symx.cu): float64 RBF, isotropic, SINGLE shape, D <= 4, bounding box given ----
+bool symx_applicable(const cagp_kernel_desc* kd, int64_t n, int k, int dp, bool bwd);
+SymShape symx_shape(bool bwd);
+int symx_fwd_launch(int dp, cagp::SymFwdArgs<double> a, int64_t n, int k, int a_begin, int a_end, cudaStream_t stream);
+int64_t symx_bwd_nparts(int64_t n, int k, int a_begin, int a_end);
+int symx_bwd_launch(int dp, cagp::SymBwdArgs<double> a, int64_t n, int k, int a_begin, int a_end, cudaStream_t stream);
+// type-generic shims (the fast path exists for double only)
+template <typename T>
+int symx_fwd_launch_any(int dp, const cagp::SymFwdArgs<T>& a, int64_t n, int k, int a_begin, int a_end, cudaStream_t stream) {
+    if constexpr (std::is_same<T, double>::value) return symx_fwd_launch(dp, a, n, k, a_begin, a_end, stream);
+    else return CAGP_OK;
+}
+template <typename T>
+int symx_bwd_launch_any(int dp, const cagp::SymBwdArgs<T>& a, T* ls_part, int64_t n, int k, int a_begin, int a_end, cudaStream_t stream) {
+    if constexpr (std::is_same<T, double>::value) {
+        cagp::SymBwdArgs<double> af = a;
+        af.ls_part = ls_part;
+        return symx_bwd_launch(dp, af, n, k, a_begin, a_end, stream);
+    } else {
+        return CAGP_OK;
+    }
+}
+
 }  // namespace cagp_host

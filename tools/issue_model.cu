@@ -4,7 +4,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
-enum Kind { NONE = 0, IADD = 1, FFMA = 2, LDS_BCAST = 3, LDS_LANE = 4, DADD = 5, LOP = 6, IMAD = 7, LDS_RAND = 8 };
+enum Kind { NONE = 0, IADD = 1, FFMA = 2, LDS_BCAST = 3, LDS_LANE = 4, DADD = 5, LOP = 6, IMAD = 7, LDS_RAND = 8,
+            I2F64 = 9, F2I64 = 10, FRND64 = 11, PRMT = 12, SHFL = 13, LDS128_LANE = 14, MOV = 15 };
 
 template <int KIND, int NUM, int DEN>  // NUM extra instrs per DEN DFMAs
 __global__ void k_mix(double* out, int iters, double a, double b) {
@@ -33,6 +34,13 @@ __global__ void k_mix(double* out, int iters, double a, double b) {
                     if (KIND == IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(xi[s]) : "r"(it));
                     if (KIND == FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(xf[s]) : "f"(1.0001f));
                     if (KIND == DADD) asm volatile("add.f64 %0, %0, %1;" : "+d"(xd[s]) : "d"(a));
+                    if (KIND == I2F64) { double v; asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(v) : "r"(xi[s])); xd[s] = v; }
+                    if (KIND == F2I64) { unsigned q; asm volatile("cvt.rni.s32.f64 %0, %1;" : "=r"(q) : "d"(acc[i])); xi[s] ^= q; }
+                    if (KIND == FRND64) { double q; asm volatile("cvt.rni.f64.f64 %0, %1;" : "=d"(q) : "d"(acc[i])); xi[s] ^= (unsigned)__double2loint(q); }
+                    if (KIND == PRMT) asm volatile("prmt.b32 %0, %0, %1, 0x5140;" : "+r"(xi[s]) : "r"(it));
+                    if (KIND == MOV) asm volatile("mov.b32 %0, %1;" : "=r"(xi[s]) : "r"(xi[(s + 1) & 3]));
+                    if (KIND == SHFL) asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(xi[s]) : "r"((it + threadIdx.x) & 31));
+                    if (KIND == LDS128_LANE) { double v, w; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(w) : "r"(tab_s + (unsigned)((threadIdx.x + it + e) & 1023) * 16u)); sink += (e == 0 && i == 0 && it == 12345678) ? v + w : 0; }
                     if (KIND == LDS_BCAST) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tab_s + (unsigned)((it + e) & 2047) * 8u)); sink += (e == 0 && i == 0 && it == 12345678) ? v : 0; }
                     if (KIND == LDS_LANE) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tab_s + (unsigned)((threadIdx.x + it + e) & 2047) * 8u)); sink += (e == 0 && i == 0 && it == 12345678) ? v : 0; }
                     if (KIND == LDS_RAND) { double v; xi[s] = xi[s] * 1664525u + 1013904223u; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tab_s + ((xi[s] >> 16) & 2047) * 8u)); sink += (e == 0 && i == 0 && it == 12345678) ? v : 0; }
@@ -128,6 +136,26 @@ int main() {
     run<LDS_LANE, 1, 8>("lds.64 per-lane consecutive", dout, sms);
     run<LDS_RAND, 1, 4>("lds.64 random 2048", dout, sms);
     run<LDS_RAND, 1, 8>("lds.64 random 2048", dout, sms);
+    run<I2F64, 1, 1>("i2f.f64.s32", dout, sms);
+    run<I2F64, 1, 2>("i2f.f64.s32", dout, sms);
+    run<I2F64, 1, 4>("i2f.f64.s32", dout, sms);
+    run<I2F64, 1, 8>("i2f.f64.s32", dout, sms);
+    run<F2I64, 1, 2>("f2i.s32.f64", dout, sms);
+    run<F2I64, 1, 4>("f2i.s32.f64", dout, sms);
+    run<F2I64, 1, 8>("f2i.s32.f64", dout, sms);
+    run<FRND64, 1, 4>("frnd.f64", dout, sms);
+    run<FRND64, 1, 8>("frnd.f64", dout, sms);
+    run<PRMT, 1, 1>("prmt", dout, sms);
+    run<PRMT, 1, 2>("prmt", dout, sms);
+    run<MOV, 1, 1>("mov", dout, sms);
+    run<SHFL, 1, 2>("shfl", dout, sms);
+    run<SHFL, 1, 4>("shfl", dout, sms);
+    run<SHFL, 1, 8>("shfl", dout, sms);
+    run<LDS128_LANE, 1, 2>("lds.128 per-lane consecutive", dout, sms);
+    run<LDS128_LANE, 1, 4>("lds.128 per-lane consecutive", dout, sms);
+    run<LDS128_LANE, 1, 8>("lds.128 per-lane consecutive", dout, sms);
+    run<IMAD, 1, 2>("imad", dout, sms);
+    run<LOP, 1, 2>("lop", dout, sms);
     run_dm<8,0>(dout, sms); run_dm<0,4>(dout, sms); run_dm<8,1>(dout, sms); run_dm<8,2>(dout, sms); run_dm<8,4>(dout, sms); run_dm<4,4>(dout, sms);
     cudaError_t e = cudaDeviceSynchronize();
     printf("status %s\n", cudaGetErrorString(e));
