@@ -56,6 +56,7 @@ _SIGNATURES = {
     "cagp_ks_blocksparse_fwd_sym_peer": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
                                                  c_int32, c_int32, POINTER(c_void_p), POINTER(c_int64), c_int32, c_int32,
                                                  c_int64, c_void_p]),
+    "cagp_ks_sym_fast_path": (c_int, [POINTER(KernelDesc), c_int64, c_int32, c_int32, c_int32]),
     "cagp_ks_bwd_sym_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int32, c_int32, c_int32, c_int32]),
     "cagp_ks_blocksparse_bwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
                                             c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -66,7 +67,8 @@ _SIGNATURES = {
                                         c_size_t, c_void_p]),
     "cagp_project_rows": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
-    "cagp_gram_mtm": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
+    "cagp_gram_ws_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "cagp_gram_mtm": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cagp_assemble_cotangent": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cagp_project_rows_bwd": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
@@ -94,8 +96,8 @@ LAUNCHES = 0
 CALLS = {}  # C entry point -> number of calls (tests use it to prove which native path ran)
 PROFILE = None
 _KERNELS_PER_CALL = {"cagp_ks_blocksparse_fwd_sym_peer": 1, "cagp_bounding_box": 1, "cagp_ks_dense_fwd": 1, "cagp_ks_dense_bwd_ls": 2, "cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
-                     "cagp_project_rows": 1, "cagp_gram_mtm": 1, "cagp_assemble_cotangent": 1,
-                     "cagp_project_rows_bwd": 1, "cagp_predict_moments": 1, "cagp_cross_cov_fwd": 1, "cagp_cross_cov_bwd": 2}
+                     "cagp_project_rows": 1, "cagp_gram_mtm": 2, "cagp_assemble_cotangent": 1,
+                     "cagp_project_rows_bwd": 1, "cagp_predict_moments": 2, "cagp_cross_cov_fwd": 1, "cagp_cross_cov_bwd": 2}
 
 
 class _timed:
@@ -295,6 +297,20 @@ def ks_blocksparse_fwd_sym_peer(family, xs, d, s, k, lengthscale, a_begin, a_end
                                                        world, me, ldm, _stream(xs)), "cagp_ks_blocksparse_fwd_sym_peer")
 
 
+def sym_fast_path(family, xs, d, k, lengthscale, bbox, backward=False) -> bool:
+    """True if the symmetric call also launches the float64 RBF fast-path kernel (csrc/ks_symx.cuh) AND the bounding
+    box proves its expanded form valid (every scaled |x|^2 < 300), i.e. the fast-path kernel does the work."""
+    if bbox is None:
+        return False
+    ls = lengthscale.reshape(-1).to(device=xs.device, dtype=xs.dtype).contiguous()
+    kd = make_desc(family, ls, xs.dtype, bbox)
+    if not load().cagp_ks_sym_fast_path(byref(kd), xs.shape[1], d, k, 1 if backward else 0):
+        return False
+    dp = xs.shape[0]
+    m = torch.maximum(bbox[:dp].abs(), bbox[dp:].abs())
+    return bool((m * m).sum() < 300.0)
+
+
 def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_end=None, bbox=None):
     """(s_bar (n), ls_bar) contributions of the tiles of blocks [a_begin, a_end), full cotangent Gt (k, n)."""
     _require_cuda(xs, s, Gt)
@@ -401,8 +417,12 @@ def gram_mtm(Mt):
     _require_cuda(Mt)
     k, m = Mt.shape
     B = torch.empty((k, k), dtype=Mt.dtype, device=Mt.device)
+    lib = load()
+    ws_bytes = lib.cagp_gram_ws_bytes(dtype_code(Mt.dtype), m, k)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=Mt.device)
     with torch.cuda.device(Mt.device), _timed("cagp_gram_mtm", Mt, m * k * k):
-        _check(load().cagp_gram_mtm(dtype_code(Mt.dtype), _ptr(Mt), m, m, k, _ptr(B), _stream(Mt)), "cagp_gram_mtm")
+        _check(lib.cagp_gram_mtm(dtype_code(Mt.dtype), _ptr(Mt), m, m, k, _ptr(B), _ptr(ws), ws_bytes, _stream(Mt)),
+               "cagp_gram_mtm")
     return B
 
 

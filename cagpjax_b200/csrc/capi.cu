@@ -11,6 +11,7 @@
 
 #include "aux_kernels.cuh"
 #include "host_common.cuh"
+#include "sym_tiling.cuh"
 
 namespace cagp_host {
 
@@ -31,16 +32,29 @@ int check_launch(const char* what) {
 }
 
 int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[64] = {0};  // per device (a process may drive several)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
     }
-    return sms;
+    return sms[dev];
 }
 
+}  // namespace cagp_host
+
+namespace cagp_host {
+// impl_gemm.cu: float64 contractions on the fp64 tensor core (gemm_dmma.cuh)
+size_t gram_ws_bytes_f64(int64_t m, int k);
+int gram_mtm_f64(const double* Mt, int64_t ldm, int64_t m, int k, double* B, void* ws, size_t ws_bytes, cudaStream_t stream);
+int assemble_cotangent_f64(const double* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total, int k,
+                           const double* W, const double* Abar, const double* cbar, const double* s, const double* yt,
+                           double* Gt, int64_t ldg, cudaStream_t stream);
+size_t predict_ws_bytes_f64(int64_t m, int k);
+int predict_moments_f64(const double* Mt, int64_t ldm, int64_t m, int k, const double* w, const double* Pinv,
+                        const double* scalars, double* mean, double* var, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace cagp_host
 
 using namespace cagp_host;
@@ -54,7 +68,7 @@ cublasHandle_t g_handles[64] = {nullptr};
 int get_handle(cudaStream_t stream, cublasHandle_t* out) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(CAGP_ERR_CUDA, "cudaGetDevice failed");
-    std::lock_guard<std::mutex> lock(g_handle_mu);
+    // the caller holds g_handle_mu until its gemm is enqueued (SetStream + gemm must not interleave between threads)
     if (!g_handles[dev]) {
         if (cublasCreate(&g_handles[dev]) != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublasCreate failed");
         cublasSetPointerMode(g_handles[dev], CUBLAS_POINTER_MODE_HOST);
@@ -157,6 +171,11 @@ int cagp_ks_blocksparse_fwd_sym_peer(const cagp_kernel_desc* kd, const void* xs,
     return sym_fwd_impl<float>(kd, xs, n, ld, d, s, k, a_begin, a_end, panels, row_begin, world, me, ldm, (cudaStream_t)stream);
 }
 
+int cagp_ks_sym_fast_path(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t backward) {
+    if (check_desc(kd, d) || n < 1 || k < 1) return 0;
+    return symx_applicable(kd, n, k, cagp_padded_dim(d), backward != 0) ? 1 : 0;
+}
+
 size_t cagp_ks_bwd_sym_ws_bytes(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t a_begin, int32_t a_end) {
     if (check_desc(kd, d) || n < 1 || k < 1) return 0;
     const bool ard = kd->n_lengthscale > 1;
@@ -205,27 +224,27 @@ int cagp_project_rows(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int
     return check_launch("project_rows_kernel");
 }
 
-int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B, cagp_stream_t stream) {
+size_t cagp_gram_ws_bytes(int32_t dtype, int64_t m, int32_t k) {
+    if (dtype != CAGP_F64 || m < 1 || k < 1) return 0;  // float32 goes through cuBLAS Sgemm, no scratch
+    return gram_ws_bytes_f64(m, k);
+}
+
+int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B, void* ws, size_t ws_bytes,
+                  cagp_stream_t stream) {
     if (!Mt || !B || m < 1 || k < 1 || ldm < m) return fail(CAGP_ERR_INVALID, "gram_mtm: bad argument");
+    if (dtype == CAGP_F64)  // hand-written DMMA kernel: lower-triangular tiles only, deterministic split-m reduction
+        return gram_mtm_f64((const double*)Mt, ldm, m, k, (double*)B, ws, ws_bytes, (cudaStream_t)stream);
+    if (dtype != CAGP_F32) return fail(CAGP_ERR_INVALID, "unknown dtype");
     if (m > 0x7fffffffLL || ldm > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "gram_mtm: m exceeds int32 (shard rows)");
     cublasHandle_t h;
+    std::unique_lock<std::mutex> lock(g_handle_mu);  // held across SetStream + gemm: one handle per device
     if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
-    // Mt row-major (k, ldm) == column-major (ldm, k) matrix M with m valid rows: B = M^T M.
-    // Measured on B200 at k = 1024, m = 1M: Dgemm(T, N) 59.9 ms vs Dsyrk 71.5 ms (and the gemm result is
-    // bitwise symmetric here); the mirror pass still enforces exact symmetry for the k x k algebra.
-    cublasStatus_t st;
-    if (dtype == CAGP_F64) {
-        const double one = 1.0, zero = 0.0;
-        st = cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, k, k, (int)m, &one, (const double*)Mt, (int)ldm, (const double*)Mt, (int)ldm, &zero, (double*)B, k);
-        if (st == CUBLAS_STATUS_SUCCESS) cagp::mirror_lower_kernel<double><<<dim3((k + 15) / 16, (k + 15) / 16), dim3(16, 16), 0, (cudaStream_t)stream>>>((double*)B, k);
-    } else if (dtype == CAGP_F32) {
-        const float one = 1.f, zero = 0.f;
-        st = cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, k, k, (int)m, &one, (const float*)Mt, (int)ldm, (const float*)Mt, (int)ldm, &zero, (float*)B, k);
-        if (st == CUBLAS_STATUS_SUCCESS) cagp::mirror_lower_kernel<float><<<dim3((k + 15) / 16, (k + 15) / 16), dim3(16, 16), 0, (cudaStream_t)stream>>>((float*)B, k);
-    } else {
-        return fail(CAGP_ERR_INVALID, "unknown dtype");
-    }
+    // Mt row-major (k, ldm) == column-major (ldm, k) matrix M with m valid rows: B = M^T M (float32 only)
+    const float one = 1.f, zero = 0.f;
+    cublasStatus_t st = cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, k, k, (int)m, &one, (const float*)Mt, (int)ldm, (const float*)Mt, (int)ldm, &zero, (float*)B, k);
+    lock.unlock();
     if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas gemm (gram) failed with status %d", (int)st);
+    cagp::mirror_lower_kernel<float><<<dim3((k + 15) / 16, (k + 15) / 16), dim3(16, 16), 0, (cudaStream_t)stream>>>((float*)B, k);
     return check_launch("mirror_lower_kernel");
 }
 
@@ -234,26 +253,24 @@ int cagp_assemble_cotangent(int32_t dtype, const void* Mt, int64_t ldm, int64_t 
                             void* Gt, int64_t ldg, cagp_stream_t stream) {
     if (!Mt || !W || !Abar || !cbar || !s || !yt || !Gt) return fail(CAGP_ERR_INVALID, "assemble_cotangent: null pointer");
     if (m < 1 || k < 1 || ldm < m || ldg < m || row_offset < 0 || row_offset + m > n_total) return fail(CAGP_ERR_INVALID, "assemble_cotangent: bad shape");
+    if (dtype == CAGP_F64)  // one DMMA kernel: W Mt with the outer terms as its epilogue
+        return assemble_cotangent_f64((const double*)Mt, ldm, m, row_offset, n_total, k, (const double*)W, (const double*)Abar,
+                                      (const double*)cbar, (const double*)s, (const double*)yt, (double*)Gt, ldg, (cudaStream_t)stream);
+    if (dtype != CAGP_F32) return fail(CAGP_ERR_INVALID, "unknown dtype");
     if (m > 0x7fffffffLL || ldm > 0x7fffffffLL || ldg > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "assemble_cotangent: m exceeds int32");
-    cublasHandle_t h;
-    if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
     cagp::BlockLayout lay{n_total, k, n_total / k};
     dim3 grid((unsigned)((m + 255) / 256), (unsigned)k);
-    cublasStatus_t st;
-    // column-major: G (m x k, ld ldg) = M (m x k, ld ldm) * W^T (k x k)  + prefilled outer terms
-    if (dtype == CAGP_F64) {
-        cagp::cotangent_prefill_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(m, row_offset, lay, (const double*)Abar, (const double*)cbar, (const double*)s, (const double*)yt, (double*)Gt, ldg);
-        const double one = 1.0;
-        st = cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const double*)Mt, (int)ldm, (const double*)W, k, &one, (double*)Gt, (int)ldg);
-    } else if (dtype == CAGP_F32) {
-        cagp::cotangent_prefill_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(m, row_offset, lay, (const float*)Abar, (const float*)cbar, (const float*)s, (const float*)yt, (float*)Gt, ldg);
-        const float one = 1.f;
-        st = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const float*)Mt, (int)ldm, (const float*)W, k, &one, (float*)Gt, (int)ldg);
-    } else {
-        return fail(CAGP_ERR_INVALID, "unknown dtype");
-    }
+    // float32: column-major G (m x k, ld ldg) = M (m x k, ld ldm) * W^T (k x k) + prefilled outer terms (cuBLAS Sgemm)
+    cagp::cotangent_prefill_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(m, row_offset, lay, (const float*)Abar, (const float*)cbar, (const float*)s, (const float*)yt, (float*)Gt, ldg);
+    if (int rc = check_launch("cotangent_prefill_kernel")) return rc;
+    cublasHandle_t h;
+    std::unique_lock<std::mutex> lock(g_handle_mu);
+    if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
+    const float one = 1.f;
+    cublasStatus_t st = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const float*)Mt, (int)ldm, (const float*)W, k, &one, (float*)Gt, (int)ldg);
+    lock.unlock();
     if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas gemm failed with status %d", (int)st);
-    return check_launch("cotangent_prefill_kernel");
+    return CAGP_OK;
 }
 
 int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total,
@@ -325,8 +342,8 @@ int cagp_cross_cov_bwd(const cagp_kernel_desc* kd, const void* xs1, int64_t m, i
 }
 
 size_t cagp_predict_ws_bytes(int32_t dtype, int64_t m, int32_t k) {
-    const size_t es = dtype == CAGP_F64 ? 8 : 4;
-    return (size_t)k * (size_t)m * es;
+    if (dtype == CAGP_F64) return predict_ws_bytes_f64(m, k);
+    return (size_t)k * (size_t)m * 4;
 }
 
 int cagp_predict_moments(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, const void* w,
@@ -334,27 +351,22 @@ int cagp_predict_moments(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, 
                          cagp_stream_t stream) {
     if (!Mt || !w || !Pinv || !scalars || !mean || !var || !ws) return fail(CAGP_ERR_INVALID, "predict_moments: null pointer");
     if (m < 1 || k < 1 || ldm < m) return fail(CAGP_ERR_INVALID, "predict_moments: bad shape");
-    if (m > 0x7fffffffLL || ldm > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "predict_moments: m exceeds int32");
     if (ws_bytes < cagp_predict_ws_bytes(dtype, m, k)) return fail(CAGP_ERR_WORKSPACE, "predict_moments: workspace too small");
+    if (dtype == CAGP_F64)  // DMMA kernel; Z = Pinv Mt is contracted in its epilogue and never written
+        return predict_moments_f64((const double*)Mt, ldm, m, k, (const double*)w, (const double*)Pinv, (const double*)scalars,
+                                   (double*)mean, (double*)var, ws, ws_bytes, (cudaStream_t)stream);
+    if (dtype != CAGP_F32) return fail(CAGP_ERR_INVALID, "unknown dtype");
+    if (m > 0x7fffffffLL || ldm > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "predict_moments: m exceeds int32");
     cublasHandle_t h;
+    std::unique_lock<std::mutex> lock(g_handle_mu);
     if (int rc = get_handle((cudaStream_t)stream, &h)) return rc;
-    cublasStatus_t st;
-    const unsigned grid = (unsigned)((m + 255) / 256);
-    // column-major: Z (m x k, ld m) = M (m x k) * Pinv (k x k, symmetric)
-    if (dtype == CAGP_F64) {
-        const double one = 1.0, zero = 0.0;
-        st = cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const double*)Mt, (int)ldm, (const double*)Pinv, k, &zero, (double*)ws, (int)m);
-        if (st == CUBLAS_STATUS_SUCCESS)
-            cagp::predict_moments_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)Mt, ldm, (const double*)ws, m, m, k, (const double*)w, (const double*)scalars, (double*)mean, (double*)var);
-    } else if (dtype == CAGP_F32) {
-        const float one = 1.f, zero = 0.f;
-        st = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const float*)Mt, (int)ldm, (const float*)Pinv, k, &zero, (float*)ws, (int)m);
-        if (st == CUBLAS_STATUS_SUCCESS)
-            cagp::predict_moments_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)Mt, ldm, (const float*)ws, m, m, k, (const float*)w, (const float*)scalars, (float*)mean, (float*)var);
-    } else {
-        return fail(CAGP_ERR_INVALID, "unknown dtype");
-    }
+    // float32: column-major Z (m x k, ld m) = M (m x k) * Pinv (k x k, symmetric) via cuBLAS Sgemm
+    const float one = 1.f, zero = 0.f;
+    cublasStatus_t st = cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, k, k, &one, (const float*)Mt, (int)ldm, (const float*)Pinv, k, &zero, (float*)ws, (int)m);
+    lock.unlock();
     if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas gemm failed with status %d", (int)st);
+    const unsigned grid = (unsigned)((m + 255) / 256);
+    cagp::predict_moments_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)Mt, ldm, (const float*)ws, m, m, k, (const float*)w, (const float*)scalars, (float*)mean, (float*)var);
     return check_launch("predict_moments_kernel");
 }
 

@@ -129,6 +129,12 @@ int cagp_ks_blocksparse_fwd_sym_peer(const cagp_kernel_desc* kd, const void* xs,
                                      void* const* panels, const int64_t* row_begin, int32_t world,
                                      int32_t me, int64_t ldm, cagp_stream_t stream);
 
+/* Introspection (host only, no launch): 1 if the symmetric forward (backward != 0: backward) call with this
+ * descriptor and shape also launches the float64-RBF fast-path kernel (csrc/ks_symx.cuh), which does the work
+ * whenever the bounding box in `kd` proves every scaled |x|^2 < 300 (decided on the device); else 0.  Tests and
+ * bench.py use it to name the kernel instance they exercise. */
+int cagp_ks_sym_fast_path(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t backward);
+
 /* Reverse mode of the symmetric forward for the same tiles, given the FULL cotangent Gt (k, ldg >= n):
  * s_bar (n) and ls_bar (n_lengthscale) receive this call's tiles' contributions (s_bar is zeroed
  * first and accumulated with atomics: sums agree to rounding, not bitwise, between runs). */
@@ -148,14 +154,18 @@ int cagp_project_rows(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int
                       int64_t n_total, int32_t k, const void* s, const void* yt, void* A, void* c,
                       cagp_stream_t stream);
 
-/* B' = M'^T M' (k, k), full symmetric matrix, via cuBLAS gemm (faster than syrk at these shapes) + mirror.  Replaces the lazy
- * inv_congruence_transform / cola.diag chain (solvers/cholesky.py:57-63, distributions.py:53-56)
- * whose trace only needs this k x k Gram matrix. */
-int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B,
-                  cagp_stream_t stream);
+/* B' = M'^T M' (k, k), full symmetric matrix.  Replaces the lazy inv_congruence_transform / cola.diag chain
+ * (solvers/cholesky.py:57-63, distributions.py:53-56) whose trace only needs this k x k Gram matrix.
+ * float64: a hand-written fp64 tensor-core kernel (mma.sync.m8n8k4.f64) that computes only the lower-triangular
+ * 128 x 128 tiles (n k^2 flops), splits the m dimension over CTAs and reduces the partial tiles from `ws`
+ * (cagp_gram_ws_bytes() bytes, caller-owned) in a fixed order; float32: cuBLAS Sgemm, ws may be NULL. */
+size_t cagp_gram_ws_bytes(int32_t dtype, int64_t m, int32_t k);
+int cagp_gram_mtm(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k, void* B, void* ws,
+                  size_t ws_bytes, cagp_stream_t stream);
 
 /* Gt = W Mt + outer terms:  Gt[b][i] = sum_c W[b][c] Mt[c][i] + Abar[blk(i)][b] s_i + cbar[b] yt_i.
- * W (k, k) row-major (the caller passes Bbar + Bbar^T).  Cotangent of M' through A', B', c'. */
+ * W (k, k) row-major (the caller passes Bbar + Bbar^T).  Cotangent of M' through A', B', c'.  float64: one fp64
+ * tensor-core kernel with the outer terms as its epilogue; float32: prefill kernel + cuBLAS Sgemm. */
 int cagp_assemble_cotangent(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,
                             int64_t n_total, int32_t k, const void* W, const void* Abar,
                             const void* cbar, const void* s, const void* yt, void* Gt, int64_t ldg,
@@ -172,7 +182,8 @@ int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m,
  *   mean[i] = mean_const + variance * sum_b M'[i, b] w[b]
  *   var[i]  = variance * kdiag - variance^2 * sum_{b,c} M'[i, b] Pinv[b][c] M'[i, c]
  * Pinv (k, k) row-major symmetric; `scalars` is a device array {variance, mean_const}.
- * `ws` holds an (k, ldm) scratch panel: cagp_predict_ws_bytes(). */
+ * `ws`: cagp_predict_ws_bytes() bytes of scratch (float64: 2 x ceil(k/128) x m partial sums - the product Pinv Mt is
+ * contracted inside the tensor-core kernel and never written; float32: a (k, m) panel for cuBLAS Sgemm). */
 size_t cagp_predict_ws_bytes(int32_t dtype, int64_t m, int32_t k);
 int cagp_predict_moments(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int32_t k,
                          const void* w, const void* Pinv, const void* scalars, void* mean, void* var,

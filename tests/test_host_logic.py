@@ -3,6 +3,7 @@
 
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -52,6 +53,56 @@ def test_header_is_plain_c(tmp_path):
         if shutil.which(cc) is None:
             pytest.skip(f"{cc} not available")
         subprocess.run([cc, *flags, "-fsyntax-only", "-I", os.path.dirname(header), str(src_c)], check=True)
+
+
+# host-only helpers of the C ABI (no launch): called through ctypes from either host language, no FFI handler needed
+_HOST_ONLY = {"cagp_last_error_string", "cagp_version", "cagp_padded_dim", "cagp_ks_sym_fast_path", "cagp_ks_bwd_ws_bytes",
+              "cagp_ks_bwd_sym_ws_bytes", "cagp_ks_dense_bwd_ls_ws_bytes", "cagp_cross_cov_bwd_ws_bytes",
+              "cagp_gram_ws_bytes", "cagp_predict_ws_bytes"}
+
+
+def test_xla_ffi_shim_is_guarded_and_covers_every_compute_symbol(tmp_path):
+    """csrc/xla_ffi_shim.cc (the JAX side of the boundary): without the XLA headers it must compile to an
+    empty translation unit; every compute entry point of the header must be called by exactly one FFI handler, and
+    jax_binding/ must register that handler."""
+    import shutil
+    import subprocess
+
+    shim = os.path.join(ROOT, "cagpjax_b200", "csrc", "xla_ffi_shim.cc")
+    src = open(shim).read()
+    if shutil.which("g++"):
+        obj = tmp_path / "shim.o"
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-c", shim, "-o", str(obj)], check=True)
+        syms = subprocess.run(["nm", str(obj)], capture_output=True, text=True).stdout
+        assert "Cagp" not in syms, "the shim must be empty when xla/ffi/api/ffi.h is absent"
+    header = open(os.path.join(ROOT, "include", "cagp_b200.h")).read()
+    declared = set(re.findall(r"\b(cagp_[a-z0-9_]+)\s*\(", header)) - {"cagp_stream_t"}
+    compute = declared - _HOST_ONLY
+    called = set(re.findall(r"\b(cagp_[a-z0-9_]+)\s*\(", src)) - {"cagp_last_error_string"}
+    assert compute == called, (sorted(compute - called), sorted(called - compute))
+    handlers = re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((Cagp\w+),", src)
+    assert len(handlers) == len(set(handlers)) == len(compute)
+    ffi_py = open(os.path.join(ROOT, "jax_binding", "cagpjax_b200_jax", "ffi.py")).read()
+    targets = dict(re.findall(r'"(Cagp\w+)":\s*"(cagp_\w+)"', ffi_py))
+    assert set(targets) == set(handlers) and set(targets.values()) == compute
+
+
+def test_jax_binding_parses_and_fails_cleanly_without_jax():
+    import ast
+    import glob
+    import importlib.util
+
+    files = sorted(glob.glob(os.path.join(ROOT, "jax_binding", "cagpjax_b200_jax", "*.py")))
+    assert len(files) >= 6
+    for f in files:
+        ast.parse(open(f).read(), f)
+    if importlib.util.find_spec("jax") is None:
+        sys.path.insert(0, os.path.join(ROOT, "jax_binding"))
+        try:
+            with pytest.raises(ImportError, match="needs jax"):
+                import cagpjax_b200_jax  # noqa: F401
+        finally:
+            sys.path.pop(0)
 
 
 def test_no_cpu_fallback_on_kernel_path():

@@ -70,7 +70,11 @@ def test_ks_bwd_matches_autograd(dtype, family, n, m, d, k, ard):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("n_total,row_offset,m,k", [(1037, 0, 1037, 10), (1037, 300, 500, 10), (9, 0, 9, 4), (50, 7, 43, 64)])
+@pytest.mark.parametrize("n_total,row_offset,m,k", [
+    (1037, 0, 1037, 10), (1037, 300, 500, 10), (9, 0, 9, 4), (50, 7, 43, 64),
+    # float64 tensor-core kernels (csrc/gemm_dmma.cuh): several 128 x 128 tiles incl. partial ones, odd leading
+    # dimensions (8-byte copy path), several m-splits of the Gram kernel, k odd
+    (3001, 0, 3001, 130), (5000, 1000, 2999, 257), (4096, 0, 4096, 256), (70000, 0, 70000, 300), (2050, 2, 2047, 129)])
 def test_row_projections(dtype, n_total, row_offset, m, k):
     g = torch.Generator().manual_seed(3)
     Mt = torch.randn(k, m, generator=g, dtype=torch.float64)
@@ -98,7 +102,8 @@ def test_row_projections(dtype, n_total, row_offset, m, k):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_predict_moments(dtype, m=700, k=12):
+@pytest.mark.parametrize("m,k", [(700, 12), (3001, 130), (4096, 256), (2047, 257)])
+def test_predict_moments(dtype, m, k):
     g = torch.Generator().manual_seed(4)
     Mt = torch.randn(k, m, generator=g, dtype=torch.float64) * 0.1
     w = torch.randn(k, generator=g, dtype=torch.float64)
