@@ -53,16 +53,21 @@ class ElboFromStats(torch.autograd.Function):
     """ELBO(A', B', c', r, q, yy, variance, sigma) with the closed-form reverse mode above."""
 
     @staticmethod
-    def forward(ctx, A, B, c, r, q, yy, variance, sigma, n, jitter):
+    def forward(ctx, A, B, c, r, q, yy, variance, sigma, n, jitter, chol=None):
         k = A.shape[0]
         s2 = sigma * sigma
         dvec = s2 * q
         dj = dvec + jitter
-        P = variance * A
-        P.diagonal().add_(dj)
-        # cholesky_ex without error checking: no host synchronisation (jnp.linalg.cholesky, which the
-        # reference uses, also returns NaNs instead of raising when P is not positive definite)
-        L = torch.linalg.cholesky_ex(P, check_errors=False).L
+        if chol is not None:
+            # the factor of exactly this P that ``init`` already computed (solvers/cholesky.py: init): the k^3
+            # factorisation is replicated on every rank, so it is paid once per step, not twice
+            L = chol
+        else:
+            P = variance * A
+            P.diagonal().add_(dj)
+            # cholesky_ex without error checking: no host synchronisation (jnp.linalg.cholesky, which the
+            # reference uses, also returns NaNs instead of raising when P is not positive definite)
+            L = torch.linalg.cholesky_ex(P, check_errors=False).L
         Q = torch.cholesky_inverse(L)
         w = Q @ r
         Bv = (variance * variance) * B
@@ -108,11 +113,14 @@ class ElboFromStats(torch.autograd.Function):
         s2_bar = -0.5 * n / s2 + 0.5 * resid / (s2 * s2) + dvecbar @ q
         sigma_bar = 2.0 * sigma * s2_bar
         return (g * variance * Pbar, g * (variance * variance) * Bvbar, g * variance * cvbar, g * rbar,
-                g * s2 * dvecbar, g * yybar, g * var_bar, g * sigma_bar, None, None)
+                g * s2 * dvecbar, g * yybar, g * var_bar, g * sigma_bar, None, None, None)
 
 
-def elbo_from_stats(A, B, c, r, q, yy, n, variance, sigma, jitter):
-    return ElboFromStats.apply(A, B, c, r, q, yy, variance, sigma, n, 0.0 if jitter is None else float(jitter))
+def elbo_from_stats(A, B, c, r, q, yy, n, variance, sigma, jitter, chol=None):
+    """``chol``: optional lower Cholesky factor of P = v A' + diag(sigma^2 q + jitter) (detached); its dependence
+    on the inputs is part of the closed-form reverse mode, so it carries no autograd edge."""
+    return ElboFromStats.apply(A, B, c, r, q, yy, variance, sigma, n, 0.0 if jitter is None else float(jitter),
+                               None if chol is None else chol.detach())
 
 
 def elbo_from_stats_dense(A, B, c, r, Qs, yy, n, variance, sigma, jitter):

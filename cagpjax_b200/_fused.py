@@ -175,38 +175,62 @@ def _gather_cotangent_for_tiles(Gt_local: torch.Tensor, shard: RowShard, out: Op
 # --------------------------------------------------------------------------------------------
 # Peer-memory forward: compute + exchange in one kernel (NVLink / NVSwitch, torch symmetric memory)
 # --------------------------------------------------------------------------------------------
-USE_PEER_MEMORY = True   # falls back to the all_to_all exchange if symmetric memory is unavailable
-_peer_panels = {}        # (group id, k, ld, dtype, device) -> (symmetric tensor, handle)
-_peer_failed = False
+USE_PEER_MEMORY = True   # falls back to the all_to_all exchange if symmetric memory is unavailable on ANY rank
+_peer_panels = {}        # (group id, k, ld, dtype, device) -> (symmetric tensor, handle) or None (unavailable)
 
 
 def _peer_panel(shard: RowShard, k: int, ld: int, dtype, device):
-    """Cached symmetric-memory scratch panel (k, ld) with its rendezvous handle (peer pointers, barrier)."""
-    import torch.distributed._symmetric_memory as symm_mem
-
+    """Cached symmetric-memory scratch panel (k, ld) with its rendezvous handle (peer pointers, barrier), or None
+    when symmetric memory cannot be set up.  Availability is decided COLLECTIVELY, once per (group, shape): every
+    rank tries the allocation + rendezvous, the outcome is min-reduced over the group, and all ranks take the same
+    branch - a rank-local fallback would leave the others waiting in the panel barrier.  Only the set-up is
+    guarded; errors of the kernel itself propagate."""
     key = (id(shard.group), k, ld, dtype, str(device))
-    ent = _peer_panels.get(key)
-    if ent is None:
+    if key in _peer_panels:
+        return _peer_panels[key]
+    import torch.distributed as dist
+
+    ent, why = None, ""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
         t = symm_mem.empty((k, ld), dtype=dtype, device=device)
         hdl = symm_mem.rendezvous(t, shard.group)
         ent = (t, hdl)
-        _peer_panels[key] = ent
+    except (RuntimeError, ImportError, AttributeError) as exc:  # no symmetric memory on this system / build
+        why = str(exc)
+    ok = torch.tensor([1 if ent is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=shard.group)
+    if int(ok.item()) == 0:
+        if shard.rank == 0:
+            import warnings
+
+            warnings.warn(f"peer-memory forward unavailable on at least one rank ({why or 'another rank failed'}); "
+                          "using the all_to_all exchange")
+        ent = None
+    _peer_panels[key] = ent
     return ent
 
 
-def sym_forward_peer(family, xs, d, s, k, lengthscale, shard: RowShard, bbox) -> torch.Tensor:
+def sym_forward_peer(family, xs, d, s, k, lengthscale, shard: RowShard, bbox, ent) -> torch.Tensor:
     """Symmetric Gram forward over the ranks of ``shard.group`` with the exchange fused into the kernel:
     column sums that belong to another rank's rows are stored straight into that rank's panel through
     peer-mapped memory.  Returns this rank's complete panel Mt (k, local rows)."""
     world, me = shard.world, shard.rank
     row_begin = [shard.peer_rows(r)[0] for r in range(world)] + [shard.n]
-    ld = max(row_begin[r + 1] - row_begin[r] for r in range(world))
-    panel, hdl = _peer_panel(shard, k, ld, xs.dtype, xs.device)
-    panel.zero_()         # column sums of row blocks split over several CTAs are accumulated atomically
+    panel, hdl = ent
+    # column sums of a row block split over several CTAs are accumulated atomically: zero exactly those rows
+    zero = N.sym_zero_rows(family, xs, d, k, lengthscale, bbox)
+    if zero == 2:
+        panel.zero_()
+    elif zero == 1:
+        panel[k - 1].zero_()
     hdl.barrier()         # every rank has zeroed its panel and finished reading it in the previous step
     N.ks_blocksparse_fwd_sym_peer(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end,
-                                  [int(p) for p in hdl.buffer_ptrs], row_begin, me, ld, bbox=bbox)
+                                  [int(p) for p in hdl.buffer_ptrs], row_begin, me, panel.shape[1], bbox=bbox)
     hdl.barrier()         # all remote stores have landed
+    # a private copy: the panel is overwritten by the next forward, Mt lives until this step's backward (and longer
+    # when a caller keeps the state for predict); 8 n k / G bytes of device copy, < 0.3 % of the step
     return panel[:, :shard.end - shard.begin].clone()
 
 
@@ -233,18 +257,15 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
         xs1 = xs
         Mt = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, bbox=bbox)
     elif shard.block_aligned and USE_SYMMETRIC:
-        global _peer_failed
         xs1 = xs
         Mt = None
-        if USE_PEER_MEMORY and not _peer_failed and shard.world <= 16:
-            try:
+        if USE_PEER_MEMORY and shard.world <= 16:
+            row_begin = [shard.peer_rows(r)[0] for r in range(shard.world)] + [shard.n]
+            ld = max(row_begin[r + 1] - row_begin[r] for r in range(shard.world))
+            ent = _peer_panel(shard, k, ld, xs.dtype, xs.device)
+            if ent is not None:
                 with N._timed("host:sym_forward_peer", xs):
-                    Mt = sym_forward_peer(family, xs, d, s, k, lengthscale, shard, bbox)
-            except (RuntimeError, ImportError, AttributeError) as exc:  # no symmetric memory on this system
-                import warnings
-
-                _peer_failed = True
-                warnings.warn(f"peer-memory forward unavailable ({exc}); using the all_to_all exchange")
+                    Mt = sym_forward_peer(family, xs, d, s, k, lengthscale, shard, bbox, ent)
         if Mt is None:
             Mfull = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, lengthscale, shard.a_begin, shard.a_end, bbox=bbox)
             Mt = exchange_tiles_to_rows(Mfull, shard)

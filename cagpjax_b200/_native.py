@@ -57,6 +57,7 @@ _SIGNATURES = {
                                                  c_int32, c_int32, POINTER(c_void_p), POINTER(c_int64), c_int32, c_int32,
                                                  c_int64, c_void_p]),
     "cagp_ks_sym_fast_path": (c_int, [POINTER(KernelDesc), c_int64, c_int32, c_int32, c_int32]),
+    "cagp_ks_fwd_sym_zero_rows": (c_int, [POINTER(KernelDesc), c_int64, c_int32, c_int32]),
     "cagp_ks_bwd_sym_ws_bytes": (c_size_t, [POINTER(KernelDesc), c_int64, c_int32, c_int32, c_int32, c_int32]),
     "cagp_ks_blocksparse_bwd_sym": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32,
                                             c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -295,6 +296,13 @@ def ks_blocksparse_fwd_sym_peer(family, xs, d, s, k, lengthscale, a_begin, a_end
     with torch.cuda.device(xs.device), _timed("cagp_ks_blocksparse_fwd_sym_peer", xs, n * n * (a_end - a_begin) // k):
         _check(load().cagp_ks_blocksparse_fwd_sym_peer(byref(kd), _ptr(xs), n, n, d, _ptr(s), k, a_begin, a_end, ptrs, rb,
                                                        world, me, ldm, _stream(xs)), "cagp_ks_blocksparse_fwd_sym_peer")
+
+
+def sym_zero_rows(family, xs, d, k, lengthscale, bbox) -> int:
+    """0 / 1 / 2: nothing / row k-1 / the whole panel must be zeroed before the peer-memory symmetric forward."""
+    ls = lengthscale.reshape(-1).to(device=xs.device, dtype=xs.dtype).contiguous()
+    kd = make_desc(family, ls, xs.dtype, bbox)
+    return int(load().cagp_ks_fwd_sym_zero_rows(byref(kd), xs.shape[1], d, k))
 
 
 def sym_fast_path(family, xs, d, k, lengthscale, bbox, backward=False) -> bool:

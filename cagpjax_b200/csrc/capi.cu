@@ -176,6 +176,20 @@ int cagp_ks_sym_fast_path(const cagp_kernel_desc* kd, int64_t n, int32_t d, int3
     return symx_applicable(kd, n, k, cagp_padded_dim(d), backward != 0) ? 1 : 0;
 }
 
+int cagp_ks_fwd_sym_zero_rows(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k) {
+    if (check_desc(kd, d) || n < 1 || k < 1) return 2;
+    const int dp = cagp_padded_dim(d);
+    const SymShape sh = sym_shape(n, k, dp, false);
+    cagp::SymTiling t = make_sym_tiling(n, k, 0, k, sh);
+    int tiles_main = t.tiles_main, tiles_last = t.tiles_last;
+    if (symx_applicable(kd, n, k, dp, false)) {
+        const cagp::SymTiling tf = make_sym_tiling(n, k, 0, k, symx_shape(false));
+        tiles_main = tf.tiles_main > tiles_main ? tf.tiles_main : tiles_main;
+        tiles_last = tf.tiles_last > tiles_last ? tf.tiles_last : tiles_last;
+    }
+    return tiles_main > 1 ? 2 : (tiles_last > 1 ? 1 : 0);
+}
+
 size_t cagp_ks_bwd_sym_ws_bytes(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t a_begin, int32_t a_end) {
     if (check_desc(kd, d) || n < 1 || k < 1) return 0;
     const bool ard = kd->n_lengthscale > 1;

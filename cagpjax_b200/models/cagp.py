@@ -216,8 +216,10 @@ class ComputationAwareGP:
         nz = state.actions.nz_values
         q = segment_sum(nz * nz, state.actions.n_blocks)
         yt = state._residual
+        L = state.cov_prior_proj_state  # lower factor of exactly P = v A' + diag(sigma^2 q) + jitter I (init)
+        chol = L.A if (isinstance(L, Triangular) and L.lower and L.A.dtype == proj.A.dtype) else None
         return elbo_from_stats(proj.A, proj.B, proj.c, state.residual_proj, q, yt @ yt, x.shape[0], var, sigma,
-                               self.solver.jitter)
+                               self.solver.jitter, chol=chol)
 
 
 def _fused_dense_statistics_ok(policy, actions, cov_xx) -> bool:

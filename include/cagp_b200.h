@@ -135,6 +135,11 @@ int cagp_ks_blocksparse_fwd_sym_peer(const cagp_kernel_desc* kd, const void* xs,
  * bench.py use it to name the kernel instance they exercise. */
 int cagp_ks_sym_fast_path(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t backward);
 
+/* Host-only: which rows of a panel the symmetric forward ACCUMULATES into (atomics, because a row block is split over
+ * several CTAs) and which the caller of the peer variant must therefore zero before the cross-rank barrier:
+ * 0 = none, 1 = row k-1 only (the overhang block), 2 = the whole panel. */
+int cagp_ks_fwd_sym_zero_rows(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k);
+
 /* Reverse mode of the symmetric forward for the same tiles, given the FULL cotangent Gt (k, ldg >= n):
  * s_bar (n) and ls_bar (n_lengthscale) receive this call's tiles' contributions (s_bar is zeroed
  * first and accumulated with atomics: sums agree to rounding, not bitwise, between runs). */

@@ -56,7 +56,7 @@ def test_header_is_plain_c(tmp_path):
 
 
 # host-only helpers of the C ABI (no launch): called through ctypes from either host language, no FFI handler needed
-_HOST_ONLY = {"cagp_last_error_string", "cagp_version", "cagp_padded_dim", "cagp_ks_sym_fast_path", "cagp_ks_bwd_ws_bytes",
+_HOST_ONLY = {"cagp_last_error_string", "cagp_version", "cagp_padded_dim", "cagp_ks_sym_fast_path", "cagp_ks_fwd_sym_zero_rows", "cagp_ks_bwd_ws_bytes",
               "cagp_ks_bwd_sym_ws_bytes", "cagp_ks_dense_bwd_ls_ws_bytes", "cagp_cross_cov_bwd_ws_bytes",
               "cagp_gram_ws_bytes", "cagp_predict_ws_bytes"}
 
