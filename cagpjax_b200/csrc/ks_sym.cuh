@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
     // uniform: expanded distance form with the replicated exp2 table (kernel_math.cuh)
     const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);
     if (p.defer_expandable && expand) return;  // uniform: the fast-path kernel (ks_symx.cuh) does this launch
+    // uniform: expanded distance q = |a|^2 + (|b|^2 - 2 a.b) for the smooth Matern families (kernel_math.cuh)
+    constexpr bool CAN_XDIST = sizeof(T) == 8 && (FAM == MATERN32 || FAM == MATERN52);
+    const bool xdist = CAN_XDIST && safe && launch_is_xdist<T, D, FAM>(p.bbox);
     unsigned tab_s;
     if constexpr (CAN_EXPAND) {
         tab_s = expand ? exptab16_load(tab, tid, nthreads) : ExpTab<T>::load(tab, tid, nthreads);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
     const BlockLayout& lay = til.lay;
     const SymRows<R, SPREAD> pl = SymRows<R, SPREAD>::make(til, blockIdx.x, tid, nthreads);
 
-    T ar[R][D], srow[R], erow[R];
+    T ar[R][D], srow[R], erow[R], narow[R];
     int64_t irow[R];
     bool valid[R];
     __syncthreads();  // the exp2 table is used below (expanded form)
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
         for (int t = 0; t < D; ++t) ar[r][t] = p.xs[t * p.ld + irow[r]];
         srow[r] = valid[r] ? p.s[irow[r]] : T(0);
         erow[r] = T(1);
+        narow[r] = T(0);
         if constexpr (CAN_EXPAND) {
             if (expand) {  // row factor 2^(-|a|^2); the column partials take s_i 2^(-|a|^2)
                 T na = T(0);
@@ -213,6 +217,12 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                 for (int t = 0; t < D; ++t) na = fma(ar[r][t], ar[r][t], na);
                 erow[r] = exp2neg16(na, tab_s);
                 srow[r] *= erow[r];
+            }
+        }
+        if constexpr (CAN_XDIST) {
+            if (xdist) {
+#pragma unroll
+                for (int t = 0; t < D; ++t) narow[r] = fma(ar[r][t], ar[r][t], narow[r]);
             }
         }
     }
@@ -251,14 +261,15 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                 for (int t = 0; t < D; ++t) {
                     const T v = in ? p.xs[t * p.ld + j] : T(0);
                     nb = fma(v, v, nb);
-                    xc[t * JC + idx] = expand ? T(-2) * v : v;
+                    xc[t * JC + idx] = (expand || xdist) ? T(-2) * v : v;
                 }
                 nbc[idx] = nb;
                 sc[idx] = in ? p.s[j] : T(0);
             }
             __syncthreads();
             auto sweep = [&](auto mode_c) {
-                constexpr int MODE = decltype(mode_c)::value;  // 0 general, 1 safe range, 2 safe + expanded form
+                // 0 general, 1 safe range, 2 safe + expanded RBF form, 3 safe + expanded distance (Matern-3/2, -5/2)
+                constexpr int MODE = decltype(mode_c)::value;
                 constexpr bool SAFE = MODE >= 1;
                 // one (thread, column) step: R kernel values feed the row sums and the column partials
                 auto pair_step = [&](int cidx, T (&cacc)[NC]) {
@@ -274,6 +285,17 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
 #pragma unroll
                             for (int tt = 0; tt < D; ++tt) u = fma(ar[r][tt], xb[tt], u);
                             const T kv = exp2neg16<true>(u, tab_s);  // K' / 2^(-|a|^2)
+                            racc[r] = fma(kv, w, racc[r]);
+                            cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
+                        }
+                    } else if constexpr (MODE == 3) {
+                        const T nb = nbc[cidx];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            T u = nb;  // |b|^2 - 2 a.b  (xb holds -2 b)
+#pragma unroll
+                            for (int tt = 0; tt < D; ++tt) u = fma(ar[r][tt], xb[tt], u);
+                            const T kv = kernel_value<T, FAM, true>(narow[r] + u, tab_s);  // fast_sqrt clamps q at 0+
                             racc[r] = fma(kv, w, racc[r]);
                             cacc[SPREAD ? r : 0] = fma(kv, srow[r], cacc[SPREAD ? r : 0]);
                         }
@@ -326,6 +348,10 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
                     if (expand) sweep(std::integral_constant<int, 2>{});
                     else if (safe) sweep(std::integral_constant<int, 1>{});
                     else sweep(std::integral_constant<int, 0>{});
+                } else if constexpr (CAN_XDIST) {
+                    if (xdist) sweep(std::integral_constant<int, 3>{});
+                    else if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
                 } else {
                     if (safe) sweep(std::integral_constant<int, 1>{});
                     else sweep(std::integral_constant<int, 0>{});
@@ -372,6 +398,9 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);  // uniform, see the forward kernel
     if (p.defer_expandable && expand) return;  // uniform: the fast-path kernel (ks_symx.cuh) does this launch
+    // uniform: expanded distance for the smooth Matern families, isotropic lengthscale (only q is needed, not q_t)
+    constexpr bool CAN_XDIST = sizeof(T) == 8 && (FAM == MATERN32 || FAM == MATERN52) && !ARD;
+    const bool xdist = CAN_XDIST && safe && launch_is_xdist<T, D, FAM>(p.bbox);
     unsigned tab_s;
     if constexpr (CAN_EXPAND) {
         tab_s = expand ? exptab16_load(tab, tid, nthreads) : ExpTab<T>::load(tab, tid, nthreads);
@@ -404,6 +433,12 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
 #pragma unroll
                 for (int t = 0; t < D; ++t) narow[r] = fma(ar[r][t], ar[r][t], narow[r]);
                 erow[r] = exp2neg16(narow[r], tab_s);
+            }
+        }
+        if constexpr (CAN_XDIST) {
+            if (xdist) {
+#pragma unroll
+                for (int t = 0; t < D; ++t) narow[r] = fma(ar[r][t], ar[r][t], narow[r]);
             }
         }
     }
@@ -451,7 +486,7 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
                 for (int t = 0; t < D; ++t) {
                     const T v = in ? p.xs[t * p.ld + j] : T(0);
                     nb = fma(v, v, nb);
-                    xc[t * JC + idx] = expand ? T(-2) * v : v;
+                    xc[t * JC + idx] = (expand || xdist) ? T(-2) * v : v;
                 }
                 nbc[idx] = nb;
                 sc[idx] = in ? p.s[j] : T(0);
@@ -461,7 +496,8 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
             }
             __syncthreads();
             auto sweep = [&](auto mode_c) {
-                constexpr int MODE = decltype(mode_c)::value;  // 0 general, 1 safe range, 2 safe + expanded form
+                // 0 general, 1 safe range, 2 safe + expanded RBF form, 3 safe + expanded distance (Matern-3/2, -5/2)
+                constexpr int MODE = decltype(mode_c)::value;
                 constexpr bool SAFE = MODE >= 1;
                 auto pair_step = [&](int cidx, T (&cacc)[NC]) {
                     T xb[D];
@@ -501,6 +537,11 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
                                 qt[tt] = df * df;
                                 q += qt[tt];
                             }
+                        } else if constexpr (MODE == 3) {
+                            T u = nbc[cidx];  // |b|^2 - 2 a.b  (xb holds -2 b)
+#pragma unroll
+                            for (int tt = 0; tt < D; ++tt) u = fma(ar[r][tt], xb[tt], u);
+                            q = fmax(narow[r] + u, T(0));  // the weight H q must not go negative by rounding
                         } else {
                             q = sqdist<T, D>(ar[r], xb);
                         }
@@ -556,6 +597,10 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
             if constexpr (sizeof(T) == 8) {
                 if constexpr (CAN_EXPAND) {
                     if (expand) sweep(std::integral_constant<int, 2>{});
+                    else if (safe) sweep(std::integral_constant<int, 1>{});
+                    else sweep(std::integral_constant<int, 0>{});
+                } else if constexpr (CAN_XDIST) {
+                    if (xdist) sweep(std::integral_constant<int, 3>{});
                     else if (safe) sweep(std::integral_constant<int, 1>{});
                     else sweep(std::integral_constant<int, 0>{});
                 } else {
