@@ -10,20 +10,24 @@
 //   gemm_wm_kernel<MOM>  predictive moments: Z = Pinv Mt is never written - the epilogue contracts it with Mt
 //                        (var_i = sum_c Mt[c][i] Z[c][i]) and with w (mean), per 128-row tile, into 2 x (k/128) x m partials.
 //
-// One CTA = 128 x 128 output tile, 256 threads = 2 x 4 warps, warp tile 64 x 32 = 8 x 4 m8n8 accumulators (128
-// registers), k-chunks of 16 staged through a 3-deep cp.async pipeline.  Shared-memory tiles are [row][k] with row
-// stride 20 doubles or [k][col] with row stride 132: both == 4 (mod 16), so the 16 lanes of a half-warp that load one
+// One CTA = 128 x 128 output tile, 512 threads = 4 x 4 warps, warp tile 32 x 32 = 4 x 4 m8n8 accumulators (64
+// registers), k-chunks of 32 double-buffered with cp.async.  (First version: 256 threads with 64 x 32 warp
+// tiles - two warps per sub-partition could not keep the DMMA pipe busy: one warp issues a DMMA every ~38 cycles,
+// the pipe takes one every 16; ncu: tensor pipe 85 % active, top stall `wait`.  Four warps per sub-partition can.)  Shared-memory tiles are [row][k] with row
+// stride 36 doubles or [k][col] with row stride 132: both == 4 (mod 16), so the 16 lanes of a half-warp that load one
 // fragment (4 k-values x 4 rows / columns, 8 bytes each) hit 16 different bank pairs.  Per k-step of 4 a warp issues
-// 12 LDS.64 for 32 DMMA (512 fp64-pipe cycles): the pipe, not shared memory, is the limit.
+// 8 LDS.64 for 16 DMMA (256 fp64-pipe cycles): the pipe, not shared memory (25 % busy), is the limit.
 #pragma once
 #include "ks_dense.cuh"
 
 namespace cagp {
 
 constexpr int kGemmTile = 128;
-constexpr int kGemmKC = 16;
-constexpr int kGemmStages = 3;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmKC = 32;     // k-chunk per pipeline stage (one CTA-wide barrier per chunk: 128 DMMA per warp between barriers)
+constexpr int kGemmStages = 2;
+constexpr int kGemmThreads = 512;
+constexpr int kGemmWM = 4, kGemmWN = 4;  // warp grid; warp tile 32 x 32
+constexpr int kGemmMT = 4, kGemmNT = 4;  // m8n8 accumulator tiles per warp
 constexpr int kGemmRS = kGemmKC + 4;     // row stride of [row][k] tiles
 constexpr int kGemmCS = kGemmTile + 4;   // row stride of [k][col] tiles
 constexpr int kGemmRowKElems = kGemmTile * kGemmRS;   // 2560 doubles
@@ -37,36 +41,36 @@ __device__ __forceinline__ void cp_async_2d(double* smem_dst, const double* gsrc
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// T[r][kk] = src[(r0 + r) * ld + k0 + kk] for r < 128, kk < 16 (zero outside rows / kend).  V16: 16-byte copies
+// T[r][kk] = src[(r0 + r) * ld + k0 + kk] for r < 128, kk < kGemmKC (zero outside rows / kend).  V16: 16-byte copies
 // (needs src 16-byte aligned, ld and k0 even).
 template <bool V16>
 __device__ __forceinline__ void gemm_load_rowk(double* __restrict__ dst, const double* __restrict__ src, int64_t ld,
                                                int64_t r0, int64_t rows, int64_t k0, int64_t kend, int tid) {
     if (V16) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = tid + kGemmThreads * e, r = idx >> 3, kk = (idx & 7) * 2;
+        for (int e = 0; e < kGemmTile * kGemmKC / 2 / kGemmThreads; ++e) {
+            const int idx = tid + kGemmThreads * e, r = idx / (kGemmKC / 2), kk = (idx % (kGemmKC / 2)) * 2;
             const bool rok = r0 + r < rows;
             const int nv = rok ? (int)max((int64_t)0, min((int64_t)2, kend - (k0 + kk))) : 0;
             cp_async_2d(dst + r * kGemmRS + kk, src + (nv ? (r0 + r) * ld + k0 + kk : 0), nv);
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int idx = tid + kGemmThreads * e, r = idx >> 4, kk = idx & 15;
+        for (int e = 0; e < kGemmTile * kGemmKC / kGemmThreads; ++e) {
+            const int idx = tid + kGemmThreads * e, r = idx / kGemmKC, kk = idx % kGemmKC;
             const bool ok = r0 + r < rows && k0 + kk < kend;
             cp_async_elem<double>(dst + r * kGemmRS + kk, src + (ok ? (r0 + r) * ld + k0 + kk : 0), ok);
         }
     }
 }
 
-// T[kk][c] = src[(k0 + kk) * ld + c0 + c] for kk < 16, c < 128 (zero outside kend / cols)
+// T[kk][c] = src[(k0 + kk) * ld + c0 + c] for kk < kGemmKC, c < 128 (zero outside kend / cols)
 template <bool V16>
 __device__ __forceinline__ void gemm_load_kcol(double* __restrict__ dst, const double* __restrict__ src, int64_t ld,
                                                int64_t k0, int64_t kend, int64_t c0, int64_t cols, int tid) {
     if (V16) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < kGemmTile * kGemmKC / 2 / kGemmThreads; ++e) {
             const int idx = tid + kGemmThreads * e, kk = idx >> 6, c = (idx & 63) * 2;
             const bool kok = k0 + kk < kend;
             const int nv = kok ? (int)max((int64_t)0, min((int64_t)2, cols - (c0 + c))) : 0;
@@ -74,7 +78,7 @@ __device__ __forceinline__ void gemm_load_kcol(double* __restrict__ dst, const d
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < kGemmTile * kGemmKC / kGemmThreads; ++e) {
             const int idx = tid + kGemmThreads * e, kk = idx >> 7, c = idx & 127;
             const bool ok = k0 + kk < kend && c0 + c < cols;
             cp_async_elem<double>(dst + kk * kGemmCS + c, src + (ok ? (k0 + kk) * ld + c0 + c : 0), ok);
@@ -82,29 +86,29 @@ __device__ __forceinline__ void gemm_load_kcol(double* __restrict__ dst, const d
     }
 }
 
-// acc (warp tile 64 x 32) += A-tile [128][16] (row-k layout) x B-tile (row-k layout [128][16] if !B_KCOL, else [16][128])
+// acc (warp tile 32 x 32) += A-tile [128][16] (row-k layout) x B-tile (row-k layout [128][16] if !B_KCOL, else [16][128])
 template <bool B_KCOL>
 __device__ __forceinline__ void gemm_mma_stage(const double* __restrict__ As, const double* __restrict__ Bs,
-                                               double (&acc)[8][4][2], int wm, int wn, int grp, int tig) {
+                                               double (&acc)[kGemmMT][kGemmNT][2], int wm, int wn, int grp, int tig) {
 #pragma unroll
     for (int ks = 0; ks < kGemmKC / 4; ++ks) {
-        double af[8], bf[4];
-        const double* ap = As + (wm * 64 + grp) * kGemmRS + ks * 4 + tig;
+        double af[kGemmMT], bf[kGemmNT];
+        const double* ap = As + (wm * 32 + grp) * kGemmRS + ks * 4 + tig;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) af[mt] = ap[mt * 8 * kGemmRS];
+        for (int mt = 0; mt < kGemmMT; ++mt) af[mt] = ap[mt * 8 * kGemmRS];
         if (B_KCOL) {
             const double* bp = Bs + (ks * 4 + tig) * kGemmCS + wn * 32 + grp;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bf[nt] = bp[nt * 8];
+            for (int nt = 0; nt < kGemmNT; ++nt) bf[nt] = bp[nt * 8];
         } else {
             const double* bp = Bs + (wn * 32 + grp) * kGemmRS + ks * 4 + tig;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bf[nt] = bp[nt * 8 * kGemmRS];
+            for (int nt = 0; nt < kGemmNT; ++nt) bf[nt] = bp[nt * 8 * kGemmRS];
         }
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt)
+        for (int mt = 0; mt < kGemmMT; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt], af[mt], bf[nt]);
+            for (int nt = 0; nt < kGemmNT; ++nt) dmma_m8n8k4(acc[mt][nt], af[mt], bf[nt]);
     }
 }
 
@@ -127,18 +131,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gram_syrk_kernel(const SyrkAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);  // [stages][2][128][20]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1, grp = lane >> 2, tig = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2, grp = lane >> 2, tig = lane & 3;
     int ta, tb;
     tri_tile(blockIdx.x, ta, tb);
     const bool diag = ta == tb;
     const int64_t a0 = (int64_t)ta * kGemmTile, b0 = (int64_t)tb * kGemmTile;
     const int64_t i_begin = (int64_t)blockIdx.y * p.chunk, i_end = min(p.m, i_begin + p.chunk);
     const int nk = (int)((i_end - i_begin + kGemmKC - 1) / kGemmKC);
-    double acc[8][4][2];
+    double acc[kGemmMT][kGemmNT][2];
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+    for (int mt = 0; mt < kGemmMT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < kGemmNT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     auto load = [&](int stage, int kt) {
         double* As = sm + stage * 2 * kGemmRowKElems;
         const int64_t k0 = i_begin + (int64_t)kt * kGemmKC;
@@ -160,8 +164,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gram_syrk_kernel(const SyrkAr
     }
     double* __restrict__ out = p.ws + (int64_t)blockIdx.y * p.k * p.k;
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
-        const int64_t r = a0 + wm * 64 + mt * 8 + grp;
+    for (int mt = 0; mt < kGemmMT; ++mt) {
+        const int64_t r = a0 + wm * 32 + mt * 8 + grp;
         if (r >= p.k) continue;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -205,16 +209,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
     double* sm = reinterpret_cast<double*>(smem_raw);  // [stages]{[128][20], [16][132]}
     constexpr int kStageElems = kGemmRowKElems + kGemmKColElems;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1, grp = lane >> 2, tig = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2, grp = lane >> 2, tig = lane & 3;
     const int bt = (int)(blockIdx.x % p.nbt);   // row tiles of one column tile run back to back (Mt tile stays in L2)
     const int64_t it = blockIdx.x / p.nbt;
     const int64_t b0 = (int64_t)bt * kGemmTile, i0 = it * kGemmTile;
     const int nk = (p.k + kGemmKC - 1) / kGemmKC;
-    double acc[8][4][2];
+    double acc[kGemmMT][kGemmNT][2];
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+    for (int mt = 0; mt < kGemmMT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < kGemmNT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     auto load = [&](int stage, int kt) {
         double* As = sm + stage * kStageElems;
         const int64_t k0 = (int64_t)kt * kGemmKC;
@@ -245,8 +249,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
             const double* __restrict__ ar0 = p.Abar + (int64_t)p.lay.block_of(p.row_offset + i) * p.k;
             const double* __restrict__ ar1 = p.Abar + (int64_t)p.lay.block_of(p.row_offset + i + (two ? 1 : 0)) * p.k;
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt) {
-                const int64_t b = b0 + wm * 64 + mt * 8 + grp;
+            for (int mt = 0; mt < kGemmMT; ++mt) {
+                const int64_t b = b0 + wm * 32 + mt * 8 + grp;
                 if (b >= p.k) continue;
                 const double cb = p.cbar[b];
                 const double v0 = acc[mt][nt][0] + fma(ar0[b], s0, cb * y0);
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
     } else {
         // per column i of the tile: sum over the tile's rows of Mt[c][i] * Z[c][i] and Mt[c][i] * w[c]
         __syncthreads();  // the pipeline buffers are free: reuse them for the cross-warp sums
-        double* red = sm;  // [2 (wm)][2 (var, mean)][128 columns]
+        double* red = sm;  // [4 (wm)][2 (var, mean)][128 columns]
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
                 double sv = 0.0, smn = 0.0;
                 if (i < p.m) {
 #pragma unroll
-                    for (int mt = 0; mt < 8; ++mt) {
-                        const int64_t c = b0 + wm * 64 + mt * 8 + grp;
+                    for (int mt = 0; mt < kGemmMT; ++mt) {
+                        const int64_t c = b0 + wm * 32 + mt * 8 + grp;
                         if (c < p.k) {
                             const double mv = p.Mt[c * p.ldm + i];
                             sv = fma(mv, acc[mt][nt][e], sv);
@@ -296,8 +300,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
         if (tid < kGemmTile) {
             const int64_t i = i0 + tid;
             if (i < p.m) {
-                p.pv[(int64_t)bt * p.m + i] = red[0 * kGemmTile + tid] + red[2 * kGemmTile + tid];
-                p.pm[(int64_t)bt * p.m + i] = red[1 * kGemmTile + tid] + red[3 * kGemmTile + tid];
+                double sv = 0.0, smn = 0.0;
+#pragma unroll
+                for (int w = 0; w < kGemmWM; ++w) {
+                    sv += red[(w * 2 + 0) * kGemmTile + tid];
+                    smn += red[(w * 2 + 1) * kGemmTile + tid];
+                }
+                p.pv[(int64_t)bt * p.m + i] = sv;
+                p.pm[(int64_t)bt * p.m + i] = smn;
             }
         }
     }

@@ -217,9 +217,14 @@ class ComputationAwareGP:
         q = segment_sum(nz * nz, state.actions.n_blocks)
         yt = state._residual
         L = state.cov_prior_proj_state  # lower factor of exactly P = v A' + diag(sigma^2 q) + jitter I (init)
-        chol = L.A if (isinstance(L, Triangular) and L.lower and L.A.dtype == proj.A.dtype) else None
-        return elbo_from_stats(proj.A, proj.B, proj.c, state.residual_proj, q, yt @ yt, x.shape[0], var, sigma,
-                               self.solver.jitter, chol=chol)
+        chol = L.A if (isinstance(L, Triangular) and L.lower and L.A.dtype == torch.float64) else None
+        # The k-sized algebra always runs in float64: it costs O(k^3) against the O(n^2) pair kernels, and in
+        # float32 it is what loses the digits (cancellation in w.B'w - tr(P^-1 B'), a Cholesky of a matrix with
+        # condition number ~1/jitter).  Mixed-dtype callers (float32 data, float64 library defaults) land here too.
+        f64 = lambda t: t.to(torch.float64)
+        out = elbo_from_stats(f64(proj.A), f64(proj.B), f64(proj.c), f64(state.residual_proj), f64(q), f64(yt @ yt),
+                              x.shape[0], f64(var), f64(sigma), self.solver.jitter, chol=chol)
+        return out.to(proj.A.dtype)
 
 
 def _fused_dense_statistics_ok(policy, actions, cov_xx) -> bool:

@@ -20,6 +20,24 @@ from ..ops import Dense, LinearOperator
 from .block_diagonal_sparse import BlockDiagonalSparse
 
 
+def _tensor_key(t: torch.Tensor):
+    """Memoisation key of a tensor's CONTENT as far as torch can tell without reading it: storage address, layout
+    and the in-place version counter.  ``id(tensor)`` (round 1) returned a stale projection after an optimiser's
+    in-place update and can be reused after a free; the memo holds a strong reference to the tensor it was computed
+    from, so the address cannot be recycled while the entry lives."""
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device))
+
+
+_MEMO_LIMIT = 4  # entries kept per operator (a training loop creates one per step when it updates in place)
+
+
+def _memo_put(memo: dict, key, value):
+    memo[key] = value
+    while len(memo) > _MEMO_LIMIT:
+        memo.pop(next(iter(memo)))
+    return value
+
+
 def _kernel_params(kernel: AbstractKernel, like: torch.Tensor):
     ls = unwrap(kernel.lengthscale).to(device=like.device, dtype=like.dtype)
     var = unwrap(kernel.variance).to(device=like.device, dtype=like.dtype)
@@ -111,7 +129,7 @@ class KernelActions(LinearOperator):
         """(k, m) unit-variance projection, differentiable w.r.t. lengthscale and nz_values."""
         if self._Mt is None:
             lz = self.lazy
-            proj = lz._projections.get(id(self.actions.nz_values))
+            proj = lz._projections.get(_tensor_key(self.actions.nz_values))
             if proj is not None and lz.is_gram and not torch.is_grad_enabled() and lz.process_group is None:
                 self._Mt = proj.Mt
             else:
@@ -245,11 +263,10 @@ class LazyKernel(LinearOperator):
         """Fused statistics of K'(X, X) S (Gram operators only); memoised per action tensor."""
         if not self.is_gram:
             raise ValueError("project() needs a Gram operator (x1 is x2)")
-        key = id(actions.nz_values)
+        key = _tensor_key(actions.nz_values)
         proj = self._projections.get(key)
         if proj is None or (residual is not None and proj.residual is not residual):
-            proj = KernelProjection(self, actions, residual)
-            self._projections[key] = proj
+            proj = _memo_put(self._projections, key, KernelProjection(self, actions, residual))
         return proj
 
     # -- products -----------------------------------------------------------------------------
@@ -264,20 +281,18 @@ class LazyKernel(LinearOperator):
         """Fused statistics of K'(X, X) S for a dense S (Gram operators only)."""
         if not self.is_gram:
             raise ValueError("project_dense() needs a Gram operator (x1 is x2)")
-        key = ("dense", id(actions.A))
+        key = ("dense",) + _tensor_key(actions.A)
         proj = self._projections.get(key)
         if proj is None or proj.residual is not residual:
-            proj = DenseKernelProjection(self, actions, residual)
-            self._projections[key] = proj
+            proj = _memo_put(self._projections, key, DenseKernelProjection(self, actions, residual))
         return proj
 
     def dense_actions(self, actions) -> KernelDenseActions:
         """K @ S for dense S, memoised per action tensor so that one kernel pass serves every consumer."""
-        key = id(actions.A)
+        key = _tensor_key(actions.A)
         op = self._dense_products.get(key)
         if op is None:
-            op = KernelDenseActions(self, actions)
-            self._dense_products[key] = op
+            op = _memo_put(self._dense_products, key, KernelDenseActions(self, actions))
         return op
 
     def _matmat(self, X: torch.Tensor) -> torch.Tensor:

@@ -49,7 +49,7 @@ Gr = ref_cot()
 t = timeit(lambda: N.assemble_cotangent(Mt, 0, m, W, Abar, cbar, s, yt)); tr = timeit(lambda: W @ Mt)
 print(f"assemble_cotangent (DMMA + fused outer terms): {t:.2f} ms = {2 * m * k * k / t / 1e9:.2f} TFLOP/s; cuBLAS gemm alone {tr:.2f} ms; rel diff {rel(G, Gr):.2e}")
 del G, Gr
-Pinv = torch.linalg.inv(Bref / m + torch.eye(k, dtype=torch.float64, device=dev))
+Pinv = torch.linalg.inv(Bref / m + torch.eye(k, dtype=torch.float64, device=dev)).contiguous()
 var, mu = torch.tensor(1.3, dtype=torch.float64, device=dev), torch.tensor(0.4, dtype=torch.float64, device=dev)
 mean, v = N.predict_moments(Mt, w, Pinv, var, mu)
 Z = Pinv @ Mt
