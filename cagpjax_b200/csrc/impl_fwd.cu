@@ -12,7 +12,8 @@ int fwd_impl(const cagp_kernel_desc* kd, const void* xs1, int64_t m, int64_t ld1
         return dispatch_family(kd->family, [&](auto fc) {
             constexpr int D = decltype(dc)::value;
             constexpr int FAM = decltype(fc)::value;
-            constexpr int R = MaxRows<D>::value;
+            // float64, D <= 4: 8 rows per thread (the per-column loads and loop control are shared by 8 pairs)
+            constexpr int R = (sizeof(T) == 8 && D <= 4) ? 8 : MaxRows<D>::value;
             constexpr int NT = 128;
             constexpr int JC = ColsPerStage<D>::value;
             cagp::FwdArgs<T> a;

@@ -143,6 +143,57 @@ __device__ __forceinline__ double exp2neg16(double u, unsigned tab_lane) {
 template <bool I2F = false>
 __device__ __forceinline__ float exp2neg16(float u, unsigned) { return u; }  // never used (fp64 only)
 
+// exp2neg16<true> for R independent arguments, written stage by stage (all R range reductions, then all R table loads, ...).
+// ptxas largely keeps this order, which (a) gives R-way instruction-level parallelism inside one warp and (b) puts
+// instructions that share a register operand - the cubic's c2, the table base - back to back, where the operand
+// reuse cache serves them: on B200 a sub-partition reads only ~two 32-bit register operands per cycle, so an fp64
+// instruction with three fresh 64-bit sources costs 3 cycles instead of 2 (profiles/r02_rf_probe.txt).
+template <int R>
+__device__ __forceinline__ void exp2neg16_vec(const double (&u)[R], unsigned tab_lane, double (&kv)[R]) {
+    constexpr double kMagic = 26388279066624.0;  // 1.5 * 2^44: ulp 2^-8
+    constexpr double c0 = 0.999999999999982504724;
+    constexpr double c1 = -0.693147180559942884057;
+    constexpr double c2 = 0.2402265436493534809523;
+    constexpr double c3 = -0.05550411375117055438833;
+    double t[R], f[R], tv[R], p[R];
+    unsigned lo[R], addr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) t[r] = u[r] + kMagic;
+#pragma unroll
+    for (int r = 0; r < R; ++r) lo[r] = (unsigned)__double2loint(t[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) f[r] = fma(__int2double_rn((int)lo[r]), -0.00390625, u[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        unsigned idx;
+        asm("and.b32 %0, %1, 255;" : "=r"(idx) : "r"(lo[r]));
+        asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr[r]) : "r"(idx), "r"(tab_lane));
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) asm("ld.shared.f64 %0, [%1];" : "=d"(tv[r]) : "r"(addr[r]));
+#pragma unroll
+    for (int r = 0; r < R; ++r) p[r] = fma(f[r], c3, c2);
+#pragma unroll
+    for (int r = 0; r < R; ++r) p[r] = fma(f[r], p[r], c1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) p[r] = fma(f[r], p[r], c0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int thi;
+        asm("mad.lo.s32 %0, %1, -4096, %2;" : "=r"(thi) : "r"(lo[r]), "r"(__double2hiint(tv[r])));
+        tv[r] = __hiloint2double(thi, __double2loint(tv[r]));
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) kv[r] = tv[r] * p[r];
+}
+
+template <int R>
+__device__ __forceinline__ void exp2neg16_vec(const float (&u)[R], unsigned, float (&kv)[R]) {  // never used (fp64 only)
+#pragma unroll
+    for (int r = 0; r < R; ++r) kv[r] = u[r];
+}
+
+
 template <bool SAFE = false>
 __device__ __forceinline__ float exp2neg(float u, unsigned) {
     float r;

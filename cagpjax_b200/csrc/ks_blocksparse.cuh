@@ -156,13 +156,25 @@ __global__ void __launch_bounds__(NT) ks_fwd_kernel(const FwdArgs<T> p) {
                 for (int j = 0; j < cl; ++j) {
                     T e[E];
                     load_entry_any<E>(cols + j * E, e);
+                    if constexpr (MODE == 2) {
+                        // stage-ordered over the R rows (kernel_math.cuh: exp2neg16_vec): instructions that share a
+                        // register operand - the column coordinate, the cubic's c2, the weight - sit back to back
+                        // and are served by the operand-reuse cache (profiles/r02_pair_kernels.md)
+                        T u[R], kv[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) u[r] = a[r][0] * e[0];  // -2 a.b
+#pragma unroll
+                        for (int t = 1; t < D; ++t)
+#pragma unroll
+                            for (int r = 0; r < R; ++r) u[r] = fma(a[r][t], e[t], u[r]);
+                        exp2neg16_vec<R>(u, tab_s, kv);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = fma(kv[r], e[D], acc[r]);
+                        continue;
+                    }
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if constexpr (MODE == 2) {
-                            T u = a[r][0] * e[0];  // -2 a.b
-#pragma unroll
-                            for (int t = 1; t < D; ++t) u = fma(a[r][t], e[t], u);
-                            acc[r] = fma(exp2neg16<true>(u, tab_s), e[D], acc[r]);
                         } else {
                             T q = T(0);
 #pragma unroll

@@ -16,7 +16,7 @@ def _softplus_inv(x):
     return x + torch.log(-torch.expm1(-x))
 
 
-def test_readme_example_training_trajectory(n_data=1000, n_actions=10, iters=60):
+def test_readme_example_training_trajectory(n_data=1000, n_actions=10, iters=250):  # BASELINE config 1: 250 AdamW iterations
     g = torch.Generator().manual_seed(42)
     x = torch.linspace(0, 10, n_data, dtype=torch.float64).reshape(-1, 1)
     y = torch.sin(x[:, 0]) + torch.randn(n_data, generator=g, dtype=torch.float64)
