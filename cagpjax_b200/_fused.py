@@ -244,8 +244,20 @@ def _box_centre(X: torch.Tensor) -> torch.Tensor:
     return torch.lerp(lo, hi, 0.5)
 
 
-def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
-    """Returns (A', B', c', Mt, xs): partial statistics over the local rows."""
+OVERLAP_GRAM = True   # B' = M'^T M' on a side stream, concurrent with the A'-dependent k x k chain (see ProjectStats)
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard, gram_stream=None):
+    """Returns (A', B', c', Mt, xs, xs1, bbox): partial statistics over the local rows.  ``gram_stream``: CUDA stream
+    on which B' is computed (after the pair kernel); the CALLER then owns the synchronisation of B'."""
     d = X.shape[1]
     # origin = centre of the bounding box: stationary kernels only see differences, and centred coordinates keep
     # |x|^2 small, which is what admits the expanded-distance fast path of the symmetric RBF kernels
@@ -275,8 +287,18 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard):
         Mt = N.ks_blocksparse_fwd(family, xs1, xs, d, s, k, lengthscale)
     sl = s[shard.begin:shard.end].contiguous()
     yl = yt[shard.begin:shard.end].contiguous()
-    A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)
-    B = N.gram_mtm(Mt)
+    if gram_stream is not None:
+        main = torch.cuda.current_stream(Mt.device)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(gram_stream):
+            gram_stream.wait_event(done)       # M' is complete
+            B = N.gram_mtm(Mt)
+        Mt.record_stream(gram_stream)
+        A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)   # main stream, concurrently
+    else:
+        A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)
+        B = N.gram_mtm(Mt)
     return A, B, c, Mt, xs, xs1, bbox
 
 
@@ -314,13 +336,34 @@ class ProjectStats(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, X, lengthscale, s, yt, family, k, shard, holder, local_fwd, local_bwd):
-        local_fwd = local_fwd or native_local_forward
-        A, B, c, *saved = local_fwd(family, X, lengthscale, s, yt, k, shard)
-        if shard.sharded:
-            packed = torch.cat([A.reshape(-1), B.reshape(-1), c.reshape(-1)])
-            _all_reduce_sum(packed, shard.group)
-            kk = k * k
-            A, B, c = packed[:kk].view(k, k), packed[kk:2 * kk].view(k, k), packed[2 * kk:]
+        # B' = M'^T M' is the longest of the HBM-bound / GEMM kernels after the pair kernel, and nothing needs it before
+        # the ELBO's closed form; the Cholesky factorisation, the solve and the KL chain only need A', c'.  With a
+        # holder to carry the event, B' (and its all-reduce) runs on a side stream and the consumer waits for it
+        # (KernelProjection.B).  Not under CUDA-graph capture (the side stream would have to re-join the capture).
+        side = None
+        if (local_fwd is None and OVERLAP_GRAM and holder is not None and X.is_cuda
+                and not torch.cuda.is_current_stream_capturing()):
+            side = _side_stream(X.device)
+        if side is not None:
+            A, B, c, *saved = native_local_forward(family, X, lengthscale, s, yt, k, shard, gram_stream=side)
+            if shard.sharded:
+                packed = torch.cat([A.reshape(-1), c.reshape(-1)])
+                _all_reduce_sum(packed, shard.group)          # issued first: NCCL runs collectives in issue order
+                A, c = packed[:k * k].view(k, k), packed[k * k:]
+                with torch.cuda.stream(side):
+                    _all_reduce_sum(B, shard.group)
+            ready = torch.cuda.Event()
+            ready.record(side)
+            B.record_stream(torch.cuda.current_stream(X.device))
+            holder["B_event"] = ready
+        else:
+            local_fwd = local_fwd or native_local_forward
+            A, B, c, *saved = local_fwd(family, X, lengthscale, s, yt, k, shard)
+            if shard.sharded:
+                packed = torch.cat([A.reshape(-1), B.reshape(-1), c.reshape(-1)])
+                _all_reduce_sum(packed, shard.group)
+                kk = k * k
+                A, B, c = packed[:kk].view(k, k), packed[kk:2 * kk].view(k, k), packed[2 * kk:]
         ctx.family, ctx.k, ctx.shard = family, k, shard
         ctx.local_bwd = local_bwd or native_local_backward
         ctx.saved_extra = saved

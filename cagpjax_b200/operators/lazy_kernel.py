@@ -73,7 +73,11 @@ class KernelProjection:
 
     @property
     def B(self):
-        return self._compute()[1]
+        B = self._compute()[1]
+        ready = self._holder.pop("B_event", None)  # B' was produced on a side stream (_fused.ProjectStats.forward)
+        if ready is not None:
+            torch.cuda.current_stream(B.device).wait_event(ready)
+        return B
 
     @property
     def c(self):

@@ -78,16 +78,21 @@ def test_elbo_gradients_match_oracle_f64(family, n, d, k, ard):
 @pytest.mark.parametrize("family", ["rbf", "matern32"])
 @pytest.mark.parametrize("n,d,k", [(9, 1, 4), (1037, 3, 10), (700, 8, 64)])
 def test_elbo_and_gradients_f32(family, n, d, k):
+    """North star: 1e-4 in float32.  The oracle (float64 arithmetic) sees the same float32-ROUNDED inputs as the
+    kernels; the pair kernels run in float32, the k-sized algebra in float64 (models/cagp.py:_elbo_fused).  Measured
+    (tools/f32_errors.py): ELBO <= 2e-7, gradients <= 1e-5."""
     model, data, p, x, y = make_problem(family, n, d, k, dtype=torch.float32, normalize=True, obs_stddev=0.5)
     val, grads = gpx.value_and_grad(neg_elbo, model, data)
     assert val.dtype == torch.float32
-    oval, ograds = O.elbo_and_grad_literal(family, x, y, p, k)
-    assert rel_err(-val, oval) < TOL[torch.float32] * 10
+    x32, y32 = data.X.double().cpu(), data.y.double().cpu().reshape(-1)
+    p.actions = gpx.unwrap(model.policy.nz_values).detach().double().cpu()
+    oval, ograds = O.elbo_and_grad_literal(family, x32, y32, p, k)
+    assert rel_err(-val, oval) < TOL[torch.float32]
     names = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev",
              "constant": "mean_constant", "nz_values": "actions"}
     for name, g in grads.items():
         key = names[name.split(".")[1]]
-        assert rel_err(-g.reshape(-1), ograds[key].reshape(-1)) < 5e-2, name
+        assert rel_err(-g.reshape(-1), ograds[key].reshape(-1)) < TOL[torch.float32], name
 
 
 def test_predict_no_inputs_equals_predict_train_inputs():
