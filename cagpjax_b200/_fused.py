@@ -212,6 +212,29 @@ def _peer_panel(shard: RowShard, k: int, ld: int, dtype, device):
     return ent
 
 
+def _peer_buffer(shard: RowShard, shape, dtype, device, tag: str):
+    """Collectively agreed symmetric-memory buffer (see _peer_panel) for other shapes, e.g. the (k, n) cotangent buffer."""
+    key = (id(shard.group), tag) + tuple(shape) + (dtype, str(device))
+    if key in _peer_panels:
+        return _peer_panels[key]
+    import torch.distributed as dist
+
+    ent = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = symm_mem.empty(tuple(shape), dtype=dtype, device=device)
+        ent = (t, symm_mem.rendezvous(t, shard.group))
+    except (RuntimeError, ImportError, AttributeError):
+        ent = None
+    ok = torch.tensor([1 if ent is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=shard.group)
+    if int(ok.item()) == 0:
+        ent = None
+    _peer_panels[key] = ent
+    return ent
+
+
 def sym_forward_peer(family, xs, d, s, k, lengthscale, shard: RowShard, bbox, ent) -> torch.Tensor:
     """Symmetric Gram forward over the ranks of ``shard.group`` with the exchange fused into the kernel:
     column sums that belong to another rank's rows are stored straight into that rank's panel through
@@ -309,8 +332,26 @@ def native_local_backward(family, X, lengthscale, s, yt, k, shard: RowShard, sav
     sl = s[shard.begin:shard.end].contiguous()
     yl = yt[shard.begin:shard.end].contiguous()
     W = (Bbar + Bbar.T).contiguous()
-    Gt = N.assemble_cotangent(Mt, shard.begin, shard.n, W, Abar.contiguous(), cbar.contiguous(), sl, yl)
     whole = shard.begin == 0 and shard.end == shard.n
+    if (not whole and shard.block_aligned and USE_SYMMETRIC and USE_PEER_MEMORY and shard.world <= 16
+            and Mt.dtype == torch.float64):
+        # compute + exchange in one kernel: the cotangent GEMM stores its panel into this rank's (k, n) tile buffer and
+        # every row b also into the buffer of the rank that owns action block b (remote stores from the epilogue)
+        ent = _peer_buffer(shard, (k, shard.n), Mt.dtype, Mt.device, "cotangent")
+        if ent is not None:
+            Gfull, hdl = ent
+            block_begin = [RowShard.block_range(k, r, shard.world)[0] for r in range(shard.world)] + [k]
+            with N._timed("host:assemble_cotangent_peer", Mt):
+                hdl.barrier()   # every rank is done reading its buffer in the previous backward
+                N.assemble_cotangent_peer(Mt, shard.begin, shard.n, W, Abar.contiguous(), cbar.contiguous(), sl, yl,
+                                          [int(p) for p in hdl.buffer_ptrs], block_begin, shard.rank, shard.n)
+                hdl.barrier()   # all remote stores have landed
+            s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gfull, lengthscale, shard.a_begin, shard.a_end,
+                                                     bbox=bbox)
+            s_dir, yt_bar = N.project_rows_bwd(Mt, shard.begin, shard.n, Abar.contiguous(), cbar.contiguous())
+            s_bar[shard.begin:shard.end] += s_dir
+            return s_bar, yt_bar, ls_bar
+    Gt = N.assemble_cotangent(Mt, shard.begin, shard.n, W, Abar.contiguous(), cbar.contiguous(), sl, yl)
     if whole and USE_SYMMETRIC:
         s_bar, ls_bar = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, bbox=bbox)
     elif shard.block_aligned and USE_SYMMETRIC:

@@ -72,6 +72,9 @@ _SIGNATURES = {
     "cagp_gram_mtm": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cagp_assemble_cotangent": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cagp_assemble_cotangent_peer": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_int32),
+                                             c_int32, c_int32, c_int64, c_void_p]),
     "cagp_project_rows_bwd": (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "cagp_ks_dense_fwd": (c_int, [POINTER(KernelDesc), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int32,
@@ -97,7 +100,7 @@ LAUNCHES = 0
 CALLS = {}  # C entry point -> number of calls (tests use it to prove which native path ran)
 PROFILE = None
 _KERNELS_PER_CALL = {"cagp_ks_blocksparse_fwd_sym_peer": 1, "cagp_bounding_box": 1, "cagp_ks_dense_fwd": 1, "cagp_ks_dense_bwd_ls": 2, "cagp_ks_blocksparse_fwd_sym": 1, "cagp_ks_blocksparse_bwd_sym": 2, "cagp_scale_inputs": 1, "cagp_ks_blocksparse_fwd": 1, "cagp_ks_blocksparse_bwd": 2,
-                     "cagp_project_rows": 1, "cagp_gram_mtm": 2, "cagp_assemble_cotangent": 1,
+                     "cagp_project_rows": 1, "cagp_gram_mtm": 2, "cagp_assemble_cotangent": 1, "cagp_assemble_cotangent_peer": 1,
                      "cagp_project_rows_bwd": 1, "cagp_predict_moments": 2, "cagp_cross_cov_fwd": 1, "cagp_cross_cov_bwd": 2}
 
 
@@ -443,6 +446,20 @@ def assemble_cotangent(Mt, row_offset, n_total, W, Abar, cbar, s_local, yt_local
                                               _ptr(Abar), _ptr(cbar), _ptr(s_local), _ptr(yt_local), _ptr(Gt), m,
                                               _stream(Mt)), "cagp_assemble_cotangent")
     return Gt
+
+
+def assemble_cotangent_peer(Mt, row_offset, n_total, W, Abar, cbar, s_local, yt_local, buffer_ptrs, block_begin, me, ld):
+    """Cotangent panel of this rank written straight into the ranks' full-width (k, ld) buffers (peer memory): its own
+    buffer gets the whole panel, the owner of action block b additionally gets row b.  float64 only."""
+    _require_cuda(Mt, W, Abar, cbar, s_local, yt_local)
+    k, m = Mt.shape
+    world = len(buffer_ptrs)
+    ptrs = (c_void_p * world)(*[c_void_p(int(p)) for p in buffer_ptrs])
+    bb = (c_int32 * (world + 1))(*[int(v) for v in block_begin])
+    with torch.cuda.device(Mt.device), _timed("cagp_assemble_cotangent_peer", Mt, 2 * m * k * k):
+        _check(load().cagp_assemble_cotangent_peer(dtype_code(Mt.dtype), _ptr(Mt), m, m, row_offset, n_total, k, _ptr(W),
+                                                   _ptr(Abar), _ptr(cbar), _ptr(s_local), _ptr(yt_local), ptrs, bb, world,
+                                                   me, ld, _stream(Mt)), "cagp_assemble_cotangent_peer")
 
 
 def project_rows_bwd(Mt, row_offset, n_total, Abar, cbar):

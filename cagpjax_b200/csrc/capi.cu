@@ -52,6 +52,10 @@ int gram_mtm_f64(const double* Mt, int64_t ldm, int64_t m, int k, double* B, voi
 int assemble_cotangent_f64(const double* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total, int k,
                            const double* W, const double* Abar, const double* cbar, const double* s, const double* yt,
                            double* Gt, int64_t ldg, cudaStream_t stream);
+int assemble_cotangent_peer_f64(const double* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total, int k,
+                                const double* W, const double* Abar, const double* cbar, const double* s, const double* yt,
+                                void* const* buffers, const int32_t* block_begin, int world, int me, int64_t ld,
+                                cudaStream_t stream);
 size_t predict_ws_bytes_f64(int64_t m, int k);
 int predict_moments_f64(const double* Mt, int64_t ldm, int64_t m, int k, const double* w, const double* Pinv,
                         const double* scalars, double* mean, double* var, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -285,6 +289,24 @@ int cagp_assemble_cotangent(int32_t dtype, const void* Mt, int64_t ldm, int64_t 
     lock.unlock();
     if (st != CUBLAS_STATUS_SUCCESS) return fail(CAGP_ERR_CUBLAS, "cublas gemm failed with status %d", (int)st);
     return CAGP_OK;
+}
+
+int cagp_assemble_cotangent_peer(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,
+                                 int64_t n_total, int32_t k, const void* W, const void* Abar, const void* cbar,
+                                 const void* s, const void* yt, void* const* buffers, const int32_t* block_begin,
+                                 int32_t world, int32_t me, int64_t ld, cagp_stream_t stream) {
+    if (!Mt || !W || !Abar || !cbar || !s || !yt || !buffers || !block_begin) return fail(CAGP_ERR_INVALID, "assemble_cotangent_peer: null pointer");
+    if (dtype != CAGP_F64) return fail(CAGP_ERR_UNSUPPORTED, "assemble_cotangent_peer: float64 only");
+    if (world < 1 || world > 16 || me < 0 || me >= world) return fail(CAGP_ERR_INVALID, "assemble_cotangent_peer: bad world/rank");
+    if (m < 1 || k < 1 || ldm < m || ld < n_total || row_offset < 0 || row_offset + m > n_total) return fail(CAGP_ERR_INVALID, "assemble_cotangent_peer: bad shape");
+    if (block_begin[0] != 0 || block_begin[world] != k) return fail(CAGP_ERR_INVALID, "assemble_cotangent_peer: block_begin must span [0, k]");
+    for (int h = 0; h < world; ++h) {
+        if (!buffers[h]) return fail(CAGP_ERR_INVALID, "assemble_cotangent_peer: null buffer");
+        if (block_begin[h + 1] < block_begin[h]) return fail(CAGP_ERR_INVALID, "assemble_cotangent_peer: bad block partition");
+    }
+    return assemble_cotangent_peer_f64((const double*)Mt, ldm, m, row_offset, n_total, k, (const double*)W, (const double*)Abar,
+                                       (const double*)cbar, (const double*)s, (const double*)yt, buffers, block_begin, world, me,
+                                       ld, (cudaStream_t)stream);
 }
 
 int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total,

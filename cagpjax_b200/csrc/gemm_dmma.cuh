@@ -189,7 +189,8 @@ __global__ void gram_reduce_kernel(const double* __restrict__ ws, int splits, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-enum GemmEpilogue : int { GEMM_COT = 0, GEMM_MOM = 1 };
+enum GemmEpilogue : int { GEMM_COT = 0, GEMM_MOM = 1, GEMM_COT_PEER = 2 };
+constexpr int kGemmMaxPeers = 16;
 
 struct GemmWmArgs {
     const double* W; int k;                     // (k, k) row-major, A operand
@@ -201,6 +202,11 @@ struct GemmWmArgs {
     int64_t row_offset; BlockLayout lay;
     // MOM: pv[bt][i] = sum_{c in tile bt} Mt[c][i] (W Mt)[c][i],  pm[bt][i] = sum_{c in tile bt} Mt[c][i] w[c]
     const double* w; double* pv; double* pm;
+    // COT_PEER (one process per GPU): every rank h holds a FULL-width buffer peer[h] (k, peer_ld >= n_total), indexed by
+    // GLOBAL row.  This rank's panel (its rows = columns [row_offset, row_offset + m) of the buffers) is stored into its
+    // own buffer, and row b additionally into the buffer of the rank that owns action block b (block_begin[h] <= b <
+    // block_begin[h + 1]) - remote st.global over NVLink, which replaces the all_to_all of the cotangent.
+    double* peer[kGemmMaxPeers]; int64_t peer_ld; int block_begin[kGemmMaxPeers + 1]; int world, me;
 };
 
 template <int EPI, bool V16>
@@ -238,8 +244,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
         const double* As = sm + (kt % kGemmStages) * kStageElems;
         gemm_mma_stage<true>(As, As + kGemmRowKElems, acc, wm, wn, grp, tig);
     }
-    if (EPI == GEMM_COT) {
-        // a lane holds two consecutive columns (i, i + 1) of 8 x 4 rows: 16-byte stores, 64 contiguous bytes per row
+    if (EPI == GEMM_COT || EPI == GEMM_COT_PEER) {
+        // a lane holds two consecutive columns (i, i + 1) of 4 x 4 rows: 16-byte stores, 64 contiguous bytes per row
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             const int64_t i = i0 + wn * 32 + nt * 8 + 2 * tig;
@@ -255,12 +261,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_wm_kernel(const GemmWmAr
                 const double cb = p.cbar[b];
                 const double v0 = acc[mt][nt][0] + fma(ar0[b], s0, cb * y0);
                 const double v1 = acc[mt][nt][1] + fma(ar1[b], s1, cb * y1);
-                double* dst = p.Gt + b * p.ldg + i;
-                if (V16 && two) {
-                    *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                auto put = [&](double* dst) {
+                    if (V16 && two) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                    } else {
+                        dst[0] = v0;
+                        if (two) dst[1] = v1;
+                    }
+                };
+                if (EPI == GEMM_COT) {
+                    put(p.Gt + b * p.ldg + i);
                 } else {
-                    dst[0] = v0;
-                    if (two) dst[1] = v1;
+                    const int64_t off = b * p.peer_ld + p.row_offset + i;
+                    put(p.peer[p.me] + off);
+                    int h = 0;
+                    while (h + 1 < p.world && (int)b >= p.block_begin[h + 1]) ++h;
+                    if (h != p.me) put(p.peer[h] + off);  // the owner of block b needs G'[j, b] for all rows j
                 }
             }
         }

@@ -55,6 +55,7 @@ static int launch_wm(int epi, const cagp::GemmWmArgs& a, bool v16, cudaStream_t 
     if (nblocks > 0x7fffffffLL) return fail(CAGP_ERR_UNSUPPORTED, "gemm_wm: too many tiles");
     void (*kern)(const cagp::GemmWmArgs);
     if (epi == cagp::GEMM_COT) kern = v16 ? cagp::gemm_wm_kernel<cagp::GEMM_COT, true> : cagp::gemm_wm_kernel<cagp::GEMM_COT, false>;
+    else if (epi == cagp::GEMM_COT_PEER) kern = v16 ? cagp::gemm_wm_kernel<cagp::GEMM_COT_PEER, true> : cagp::gemm_wm_kernel<cagp::GEMM_COT_PEER, false>;
     else kern = v16 ? cagp::gemm_wm_kernel<cagp::GEMM_MOM, true> : cagp::gemm_wm_kernel<cagp::GEMM_MOM, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWmSmem) != cudaSuccess)
         return fail(CAGP_ERR_CUDA, "gemm_wm_kernel: shared memory opt-in failed");
@@ -71,6 +72,25 @@ int assemble_cotangent_f64(const double* Mt, int64_t ldm, int64_t m, int64_t row
     a.lay = cagp::BlockLayout{n_total, k, n_total / k};
     const bool v16 = aligned16(Mt) && aligned16(W) && aligned16(Gt) && ldm % 2 == 0 && ldg % 2 == 0 && k % 2 == 0;
     return launch_wm(cagp::GEMM_COT, a, v16, stream);
+}
+
+int assemble_cotangent_peer_f64(const double* Mt, int64_t ldm, int64_t m, int64_t row_offset, int64_t n_total, int k,
+                                const double* W, const double* Abar, const double* cbar, const double* s, const double* yt,
+                                void* const* buffers, const int32_t* block_begin, int world, int me, int64_t ld,
+                                cudaStream_t stream) {
+    cagp::GemmWmArgs a{};
+    a.W = W; a.k = k; a.Mt = Mt; a.ldm = ldm; a.m = m; a.nbt = tiles(k);
+    a.Abar = Abar; a.cbar = cbar; a.s = s; a.yt = yt; a.row_offset = row_offset;
+    a.lay = cagp::BlockLayout{n_total, k, n_total / k};
+    a.peer_ld = ld; a.world = world; a.me = me;
+    bool v16 = aligned16(Mt) && aligned16(W) && ldm % 2 == 0 && ld % 2 == 0 && k % 2 == 0 && row_offset % 2 == 0;
+    for (int h = 0; h < world; ++h) {
+        a.peer[h] = (double*)buffers[h];
+        a.block_begin[h] = block_begin[h];
+        v16 = v16 && aligned16(buffers[h]);
+    }
+    a.block_begin[world] = block_begin[world];
+    return launch_wm(cagp::GEMM_COT_PEER, a, v16, stream);
 }
 
 size_t predict_ws_bytes_f64(int64_t m, int k) { return (size_t)2 * tiles(k) * m * sizeof(double); }

@@ -128,6 +128,21 @@ ffi::Error AssembleCotangent(cudaStream_t st, Buf Mt, Buf W, Buf Abar, Buf cbar,
                                         Abar.untyped_data(), cbar.untyped_data(), s.untyped_data(), yt.untyped_data(),
                                         Gt->untyped_data(), m, st));
 }
+// ---- cagp_assemble_cotangent_peer: peer buffer addresses / block partition as int64 attribute spans -------------------
+ffi::Error AssembleCotangentPeer(cudaStream_t st, Buf Mt, Buf W, Buf Abar, Buf cbar, Buf s, Buf yt, Out own_buffer,
+                                 int64_t row_offset, int64_t n_total, ffi::Span<const int64_t> buffers,
+                                 ffi::Span<const int64_t> block_begin, int64_t me) {
+  const int64_t k = Mt.dimensions()[0], m = Mt.dimensions()[1];
+  const int world = (int)buffers.size();
+  std::vector<void*> ptrs(world);
+  std::vector<int32_t> bb(world + 1);
+  for (int r = 0; r < world; ++r) ptrs[r] = r == me ? own_buffer->untyped_data() : reinterpret_cast<void*>(buffers[r]);
+  for (int r = 0; r <= world; ++r) bb[r] = (int32_t)block_begin[r];
+  return status(cagp_assemble_cotangent_peer(dtype_of(Mt), Mt.untyped_data(), m, m, row_offset, n_total, (int32_t)k,
+                                             W.untyped_data(), Abar.untyped_data(), cbar.untyped_data(), s.untyped_data(),
+                                             yt.untyped_data(), ptrs.data(), bb.data(), world, (int32_t)me,
+                                             own_buffer->dimensions()[1], st));
+}
 // ---- cagp_project_rows_bwd -------------------------------------------------------------------------------------------
 ffi::Error ProjectRowsBwd(cudaStream_t st, Buf Mt, Buf Abar, Buf cbar, Out s_dir, Out yt_bar, int64_t row_offset, int64_t n_total) {
   const int64_t k = Mt.dimensions()[0], m = Mt.dimensions()[1];
@@ -194,6 +209,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpProjectRows, ProjectRows, CAGP_BIND() ARG ARG 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpGramMtm, GramMtm, CAGP_BIND() ARG RET RET);
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpAssembleCotangent, AssembleCotangent,
                               CAGP_BIND() ARG ARG ARG ARG ARG ARG RET I64("row_offset") I64("n_total"));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpAssembleCotangentPeer, AssembleCotangentPeer,
+                              CAGP_BIND() ARG ARG ARG ARG ARG ARG RET I64("row_offset") I64("n_total")
+                                  .Attr<ffi::Span<const int64_t>>("buffers")
+                                  .Attr<ffi::Span<const int64_t>>("block_begin") I64("me"));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpProjectRowsBwd, ProjectRowsBwd, CAGP_BIND() ARG ARG ARG RET RET I64("row_offset") I64("n_total"));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpPredictMoments, PredictMoments, CAGP_BIND() ARG ARG ARG ARG RET RET RET);
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpKsDenseFwd, KsDenseFwd, CAGP_BIND() ARG ARG ARG ARG RET I64("family") I64("d"));

@@ -176,6 +176,20 @@ int cagp_assemble_cotangent(int32_t dtype, const void* Mt, int64_t ldm, int64_t 
                             const void* cbar, const void* s, const void* yt, void* Gt, int64_t ldg,
                             cagp_stream_t stream);
 
+/* Peer-memory variant of cagp_assemble_cotangent for one-process-per-GPU runs (float64): compute and exchange are ONE
+ * kernel.  Every rank h holds a full-width buffer buffers[h] (k, ld >= n_total) indexed by GLOBAL row; this rank's panel
+ * (global rows [row_offset, row_offset + m)) is stored into its own buffer and row b additionally - remote st.global
+ * over NVLink / NVSwitch, from the GEMM epilogue - into the buffer of the rank that owns action block b
+ * (block_begin[h] <= b < block_begin[h+1]; `buffers`, `block_begin` are HOST arrays of world resp. world + 1 entries,
+ * pointers valid on THIS device, e.g. symmetric memory).  Afterwards buffers[me] holds what
+ * cagp_ks_blocksparse_bwd_sym needs for this rank's tiles (G'[i in own rows, :] and G'[:, a in own blocks]), which
+ * replaces the all-to-all of the cotangent.  A cross-rank barrier must separate the previous use of the buffers, this
+ * call, and the backward kernel. */
+int cagp_assemble_cotangent_peer(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,
+                                 int64_t n_total, int32_t k, const void* W, const void* Abar, const void* cbar,
+                                 const void* s, const void* yt, void* const* buffers, const int32_t* block_begin,
+                                 int32_t world, int32_t me, int64_t ld, cagp_stream_t stream);
+
 /* Direct (non-kernel) cotangents of the projections for the caller's m rows:
  *   s_dir[i] = sum_b Abar[blk(i)][b] M'[i, b],   yt_bar[i] = sum_b cbar[b] M'[i, b]. */
 int cagp_project_rows_bwd(int32_t dtype, const void* Mt, int64_t ldm, int64_t m, int64_t row_offset,

@@ -21,6 +21,7 @@ TARGETS = {
     "CagpProjectRows": "cagp_project_rows",
     "CagpGramMtm": "cagp_gram_mtm",
     "CagpAssembleCotangent": "cagp_assemble_cotangent",
+    "CagpAssembleCotangentPeer": "cagp_assemble_cotangent_peer",
     "CagpProjectRowsBwd": "cagp_project_rows_bwd",
     "CagpPredictMoments": "cagp_predict_moments",
     "CagpKsDenseFwd": "cagp_ks_dense_fwd",

@@ -86,3 +86,31 @@ def test_large_size_properties():
     rows = torch.arange(0, n, 997, device=DEV)
     ref = O.projected_kernel_blocksparse("rbf", X[rows].cpu().numpy(), X.cpu().numpy(), np.ones(1), s1.cpu().numpy(), k)
     assert rel_err(M1[:, rows].T, ref) < 1e-11
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("n,k", [(3001, 130), (2048, 64), (900, 7)])
+def test_peer_cotangent_gemm_emulated_ranks(world, n, k):
+    """cagp_assemble_cotangent_peer with the ranks emulated one after another on one GPU (plain buffers stand in for the
+    peer-mapped ones): afterwards rank h's (k, n) buffer holds G'[i in own rows, :] and G'[:, a in own blocks] -
+    exactly what its symmetric backward tiles read - and agrees with the unsharded cotangent."""
+    g = torch.Generator().manual_seed(5)
+    dt = torch.float64
+    Mt = (torch.randn(k, n, generator=g, dtype=dt) * 0.3).to(DEV)
+    W = torch.randn(k, k, generator=g, dtype=dt).to(DEV)
+    Abar = torch.randn(k, k, generator=g, dtype=dt).to(DEV)
+    cbar = torch.randn(k, generator=g, dtype=dt).to(DEV)
+    s = torch.randn(n, generator=g, dtype=dt).to(DEV)
+    yt = torch.randn(n, generator=g, dtype=dt).to(DEV)
+    G_ref = N.assemble_cotangent(Mt, 0, n, W, Abar, cbar, s, yt)            # (k, n), unsharded
+    shards = [_fused.RowShard.for_rank_blocks(n, k, r, world) for r in range(world)]
+    block_begin = [sh.a_begin for sh in shards] + [k]
+    bufs = [torch.full((k, n), float("nan"), dtype=dt, device=DEV) for _ in range(world)]
+    for r, sh in enumerate(shards):
+        Ml = Mt[:, sh.begin:sh.end].contiguous()
+        N.assemble_cotangent_peer(Ml, sh.begin, n, W, Abar, cbar, s[sh.begin:sh.end].contiguous(),
+                                  yt[sh.begin:sh.end].contiguous(), [b.data_ptr() for b in bufs], block_begin, r, n)
+    torch.cuda.synchronize()
+    for r, sh in enumerate(shards):
+        assert rel_err(bufs[r][:, sh.begin:sh.end], G_ref[:, sh.begin:sh.end]) < 1e-13     # own rows, all blocks
+        assert rel_err(bufs[r][sh.a_begin:sh.a_end], G_ref[sh.a_begin:sh.a_end]) < 1e-13   # own blocks, all rows
