@@ -633,9 +633,11 @@ class DenseProjectStats(torch.autograd.Function):
         yt_bar[shard.begin:shard.end] = M @ cbar
         if shard.sharded:
             n, k = S.shape
-            packed = torch.cat([S_bar.reshape(-1), yt_bar, ls_bar.reshape(-1)])
+            # S_bar (n x k: 4.1 GB at BASELINE config 5) is reduced in place; only the small vectors are packed
+            _all_reduce_sum(S_bar, shard.group)
+            packed = torch.cat([yt_bar, ls_bar.reshape(-1)])
             _all_reduce_sum(packed, shard.group)
-            S_bar, yt_bar, ls_bar = packed[:n * k].view(n, k), packed[n * k:n * k + n], packed[n * k + n:]
+            yt_bar, ls_bar = packed[:n], packed[n:]
         return None, ls_bar.reshape(lengthscale.shape), S_bar, yt_bar, None, None, None, None
 
 
