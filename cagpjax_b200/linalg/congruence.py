@@ -60,8 +60,10 @@ class ProjectedDenseGram(LinearOperator):
     def to_dense(self) -> torch.Tensor:
         from ..operators.lazy_kernel import _kernel_params
 
+        from ..operators.lazy_kernel import _tensor_key
+
         S = self.actions.A
-        proj = self.lazy._projections.get(("dense", id(S)))
+        proj = self.lazy._projections.get(("dense",) + _tensor_key(S))
         if proj is not None:  # statistics of the (possibly row-sharded) fused pass registered by init
             out = _kernel_params(self.lazy.kernel, self.lazy.x1)[1] * proj.A
         else:

@@ -145,7 +145,14 @@ def test_dense_actions_match_oracle(family, n, d, k):
         q = model.predict(st)
         assert rel_err(q.mean, om) < 1e-9 and rel_err(q.variance, ov) < 1e-9
         assert rel_err(model.prior_kl(st), O.cagp_prior_kl(ost)) < 1e-8
+    from cagpjax_b200 import _native
+
+    calls0 = dict(_native.CALLS)
     val, grads = gpx.value_and_grad(neg_elbo, model, data)
+    # one step = at most one K S pass forward + one K^T Mbar pass and one lengthscale pass backward: the memoised
+    # product must be found by every consumer (a missed memo key re-runs an n^2 k pass: round 2 lost 8x at C5 to that)
+    dense_calls = _native.CALLS.get("cagp_ks_dense_fwd", 0) - calls0.get("cagp_ks_dense_fwd", 0)
+    assert dense_calls <= 2, dense_calls
     oval, ograds = O.elbo_and_grad_literal(family, x, y, p, None)
     assert rel_err(-val, oval) < 1e-10
     key_of = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev", "constant": "mean_constant", "actions": "actions"}

@@ -72,13 +72,14 @@ def main():
             pipe_cyc = avg("smsp__pipe_fp64_cycles_active.sum")
             thread_inst = sum((f64(m) if is64 else f32(m)) for _, m in work) / len(work)
             dmma = is64 and "dense" in entry
-            # DMMA kernels: the d-op thread instructions miss the tensor instructions, count pipe cycles x 16 lanes instead
-            fp_inst = pipe_cyc * 16.0 if dmma else thread_inst
+            # DMMA kernels: the d-op thread-instruction counters miss the tensor instructions and this capture has no
+            # tensor-pipe counter, so no executed-instruction figure is derived for them (bench.py then reports frac null)
+            fp_inst = None if dmma else thread_inst
             short = re.sub(r"\(.*$", "", nm).replace("void ", "").replace("cagp::", "")
             table[entry] = {
                 "kernel": short, "launches_captured": len(work), "pairs_per_launch": pairs,
-                "fp_inst_per_pair": fp_inst / pairs,
-                "fp_inst_definition": "fp64 pipe active cycles x 16 lanes (DMMA kernel)" if dmma else
+                "fp_inst_per_pair": None if fp_inst is None else fp_inst / pairs,
+                "fp_inst_definition": "not derived: DMMA kernel (d-op counters exclude tensor instructions)" if dmma else
                                       ("DADD+DFMA+DMUL" if is64 else "FADD+FFMA+FMUL") + " thread instructions",
                 "fp64_pipe_active_pct": 100.0 * pipe_cyc / max(avg("smsp__cycles_elapsed.sum"), 1.0) if is64 else None,
                 "xu_thread_inst_per_pair": avg("smsp__thread_inst_executed_pipe_xu_pred_on.sum") / pairs,
@@ -104,7 +105,7 @@ def main():
     json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
     for c, t in out["configs"].items():
         for e, v in t.items():
-            print(f"{c:6s} {e:32s} {v['kernel'][:60]:60s} fp/pair {v['fp_inst_per_pair']:.3f}  pipe {v['fp64_pipe_active_pct']}  dram {v['dram_bytes_per_launch'] / 1e9:.2f} GB")
+            print(f"{c:6s} {e:32s} {v['kernel'][:60]:60s} fp/pair {v['fp_inst_per_pair']}  pipe {v['fp64_pipe_active_pct']}  dram {v['dram_bytes_per_launch'] / 1e9:.2f} GB")
 
 
 if __name__ == "__main__":
