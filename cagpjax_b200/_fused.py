@@ -267,8 +267,14 @@ def _box_centre(X: torch.Tensor) -> torch.Tensor:
     return torch.lerp(lo, hi, 0.5)
 
 
-OVERLAP_GRAM = True   # B' = M'^T M' on a side stream, concurrent with the A'-dependent k x k chain (see ProjectStats)
+import os as _os
+
+# B' = M'^T M' on a side stream, concurrent with the A'-dependent k x k chain (see ProjectStats).  OFF by default:
+# measured (r02) no gain at C3 on 1 GPU (1143.2 vs 1143.3 ms), -0.5 ms of 582 on 2 GPUs, and a REGRESSION on small
+# steps (C2: 46.3 vs 37.1 ms per step when steps are enqueued back to back).  CAGP_OVERLAP_GRAM=1 enables it.
+OVERLAP_GRAM = _os.environ.get("CAGP_OVERLAP_GRAM", "0") == "1"
 _side_streams = {}
+_pending_side = []   # (completion event, tensors the side stream reads): kept alive until the main stream is ordered after it
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
@@ -317,7 +323,6 @@ def native_local_forward(family, X, lengthscale, s, yt, k, shard: RowShard, gram
         with torch.cuda.stream(gram_stream):
             gram_stream.wait_event(done)       # M' is complete
             B = N.gram_mtm(Mt)
-        Mt.record_stream(gram_stream)
         A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)   # main stream, concurrently
     else:
         A, c = N.project_rows(Mt, shard.begin, shard.n, sl, yl)
@@ -386,6 +391,13 @@ class ProjectStats(torch.autograd.Function):
                 and not torch.cuda.is_current_stream_capturing()):
             side = _side_stream(X.device)
         if side is not None:
+            # side-stream work of earlier steps: order the main stream after it before its operands can be recycled
+            # (no Tensor.record_stream: that defers block reuse in the caching allocator and cost 60 % at C2)
+            main = torch.cuda.current_stream(X.device)
+            for ev, _keep in _pending_side:
+                if not ev.query():
+                    main.wait_event(ev)
+            _pending_side.clear()
             A, B, c, *saved = native_local_forward(family, X, lengthscale, s, yt, k, shard, gram_stream=side)
             if shard.sharded:
                 packed = torch.cat([A.reshape(-1), c.reshape(-1)])
@@ -395,8 +407,8 @@ class ProjectStats(torch.autograd.Function):
                     _all_reduce_sum(B, shard.group)
             ready = torch.cuda.Event()
             ready.record(side)
-            B.record_stream(torch.cuda.current_stream(X.device))
             holder["B_event"] = ready
+            _pending_side.append((ready, (saved[0], B)))   # M' and B' stay referenced until the side stream is done
         else:
             local_fwd = local_fwd or native_local_forward
             A, B, c, *saved = local_fwd(family, X, lengthscale, s, yt, k, shard)
