@@ -170,3 +170,31 @@ def test_expanded_form_falls_back_for_wide_data():
     xs = N.scale_inputs("rbf", xd, ls.to(DEV), 0.5 * (xd.amin(0) + xd.amax(0)))
     Mt = N.ks_blocksparse_fwd_sym("rbf", xs, d, s.to(DEV), k, ls.to(DEV), bbox=N.bounding_box(xs))
     assert rel_err(Mt.T, ref) < 1e-10
+
+
+@pytest.mark.parametrize("family,n,d,k", [("rbf", 2300, 3, 2), ("rbf", 1500, 2, 1), ("rbf", 977, 3, 5), ("matern32", 900, 8, 5)])
+def test_symmetric_kernels_stay_inside_their_outputs(family, n, d, k):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with canaries: the output panel
+    sits between two guard rows of NaN inside one allocation, inputs are followed by NaN padding, and every
+    result must be finite while the guards stay untouched (fast-path and general kernels, split blocks included)."""
+    g = torch.Generator().manual_seed(9)
+    X = (torch.rand(n, d, generator=g, dtype=torch.float64) * 3).to(DEV)
+    s_pad = torch.full((n + 64,), float("nan"), dtype=torch.float64, device=DEV)
+    s_pad[:n] = torch.randn(n, generator=g, dtype=torch.float64).to(DEV)
+    s = s_pad[:n]
+    ls = torch.ones(1, dtype=torch.float64, device=DEV)
+    xs = N.scale_inputs(family, X, ls, X[0])
+    bb = N.bounding_box(xs)
+    buf = torch.full((k + 2, n), float("nan"), dtype=torch.float64, device=DEV)
+    out = buf[1:k + 1]
+    out.zero_()
+    Mt = N.ks_blocksparse_fwd_sym(family, xs, d, s, k, ls, out=out, bbox=bb)
+    assert Mt.data_ptr() == out.data_ptr() and torch.isfinite(out).all()
+    assert torch.isnan(buf[0]).all() and torch.isnan(buf[k + 1]).all()
+    ref = N.ks_blocksparse_fwd(family, xs, xs, d, s, k, ls)
+    assert rel_err(out, ref) < 1e-11
+    G = torch.randn(k, n, generator=g, dtype=torch.float64).to(DEV)
+    sb, lb = N.ks_blocksparse_bwd_sym(family, xs, d, s, k, G, ls, bbox=bb)
+    sbr, lbr = N.ks_blocksparse_bwd(family, xs, xs, d, s, k, G, ls)
+    assert torch.isfinite(sb).all() and rel_err(sb, sbr) < 1e-11 and rel_err(lb, lbr) < 1e-11
+    assert torch.isnan(s_pad[n:]).all()

@@ -114,3 +114,8 @@ def test_peer_cotangent_gemm_emulated_ranks(world, n, k):
     for r, sh in enumerate(shards):
         assert rel_err(bufs[r][:, sh.begin:sh.end], G_ref[:, sh.begin:sh.end]) < 1e-13     # own rows, all blocks
         assert rel_err(bufs[r][sh.a_begin:sh.a_end], G_ref[sh.a_begin:sh.a_end]) < 1e-13   # own blocks, all rows
+        # nothing else was written: the rest of the buffer still holds the NaN canary
+        mask = torch.ones((k, n), dtype=torch.bool, device=DEV)
+        mask[:, sh.begin:sh.end] = False
+        mask[sh.a_begin:sh.a_end] = False
+        assert torch.isnan(bufs[r][mask]).all()
