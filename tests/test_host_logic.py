@@ -346,3 +346,25 @@ def test_bench_contract_on_cpu():
         prod = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                               capture_output=True, text=True, cwd=ROOT, timeout=300)
         assert prod.returncode != 0 and "no CPU fallback" in (prod.stderr + prod.stdout)
+
+
+def test_interop_wrapper_roundtrip():
+    """reference interop.py:13-81 / tests/test_operators.py TestUtils: lazify returns an operator of the same shape and
+    dtype; the lineax-shaped wrapper exposes mv / as_matrix / transpose / structures and the PSD tag."""
+    from cagpjax_b200.interop import ColaLinearOperator, is_positive_semidefinite, is_symmetric, lazify, to_lineax
+
+    A = torch.randn(5, 3, dtype=torch.float64)
+    op = lazify(A)
+    assert op.shape == (5, 3) and op.dtype == torch.float64
+    w = to_lineax(op)
+    assert isinstance(w, ColaLinearOperator) and lazify(w) is op and to_lineax(w) is w
+    v = torch.randn(3, dtype=torch.float64)
+    assert torch.allclose(w.mv(v), A @ v) and torch.equal(w.as_matrix(), A)
+    assert torch.equal(w.transpose().as_matrix(), A.T)
+    assert w.in_structure() == ((3,), torch.float64) and w.out_structure() == ((5,), torch.float64)
+    assert not is_symmetric(w)
+    P = ops.PSD(ops.Dense(A.T @ A))
+    assert is_symmetric(to_lineax(P)) and is_positive_semidefinite(to_lineax(P))
+    d = ops.Diagonal(torch.arange(1.0, 4.0, dtype=torch.float64))
+    assert lazify(to_lineax(d)) is d
+    assert to_lineax(A).as_matrix().shape == (5, 3)
