@@ -327,6 +327,23 @@ __device__ __forceinline__ bool launch_is_expandable(const T* __restrict__ bbox)
     return s < T(300);  // false for NaN
 }
 
+// Level of the expanded RBF form for the fast-path kernels (ks_symx.cuh): 1 = every |x|^2 < 300 (as above), 2 = every
+// |x|^2 < 900: u = |b|^2 - 2 a.b can then exceed the ~1000 the exponent adjustment of exp2neg16 can represent, so u is
+// clamped at 1000 first (one DMNMX more per pair; the true K' = 2^(-|a|^2 - u) is < 2^-1000 there anyway), and
+// 2^(-u) <= 2^900 keeps the row sums finite.  Rounding error of u: a few ulp of 2700, < 1e-12 relative in K'.
+// 0 = not expandable (the general kernel runs).  With the box centred, level 2 covers lengthscales down to
+// ~0.25 at C3's domain (level 1: ~0.43).
+template <typename T, int D, int FAM>
+__device__ __forceinline__ int launch_expand_level(const T* __restrict__ bbox) {
+    if (sizeof(T) == 4 || bbox == nullptr || FAM != RBF) return 0;
+    T s = T(0);
+    for (int t = 0; t < D; ++t) {
+        const T m = fmax(fabs(bbox[t]), fabs(bbox[D + t]));
+        s = fma(m, m, s);
+    }
+    return s < T(300) ? 1 : (s < T(900) ? 2 : 0);  // 0 for NaN
+}
+
 // Launch-wide proof for the EXPANDED DISTANCE of the smooth Matern families (fp64, Matern-3/2 and -5/2):
 //   q = |a - b|^2 = |a|^2 + (|b|^2 - 2 a.b),
 // a D-term FMA chain started at |b|^2 plus one add, instead of D subtractions + D FMAs.  The cancellation costs an

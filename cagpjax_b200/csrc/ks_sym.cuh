@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(256) ks_sym_fwd_kernel(const SymFwdArgs<T> p) 
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     // uniform: expanded distance form with the replicated exp2 table (kernel_math.cuh)
     const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);
-    if (p.defer_expandable && expand) return;  // uniform: the fast-path kernel (ks_symx.cuh) does this launch
+    // uniform: the fast-path kernel (ks_symx.cuh) does this launch (it also covers |x|^2 < 900 with a clamp)
+    if (p.defer_expandable && launch_expand_level<T, D, FAM>(p.bbox) > 0) return;
     // uniform: expanded distance q = |a|^2 + (|b|^2 - 2 a.b) for the smooth Matern families (kernel_math.cuh)
     constexpr bool CAN_XDIST = sizeof(T) == 8 && (FAM == MATERN32 || FAM == MATERN52);
     const bool xdist = CAN_XDIST && safe && launch_is_xdist<T, D, FAM>(p.bbox);
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(256) ks_sym_bwd_kernel(const SymBwdArgs<T> p) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nw = nthreads >> 5;
     const bool safe = launch_is_safe<T, D, FAM>(p.bbox);  // uniform: no clamp needed in exp2neg
     const bool expand = CAN_EXPAND && launch_is_expandable<T, D, FAM>(p.bbox);  // uniform, see the forward kernel
-    if (p.defer_expandable && expand) return;  // uniform: the fast-path kernel (ks_symx.cuh) does this launch
+    if (p.defer_expandable && launch_expand_level<T, D, FAM>(p.bbox) > 0) return;  // uniform: ks_symx.cuh does this launch
     // uniform: expanded distance for the smooth Matern families, isotropic lengthscale (only q is needed, not q_t)
     constexpr bool CAN_XDIST = sizeof(T) == 8 && (FAM == MATERN32 || FAM == MATERN52) && !ARD;
     const bool xdist = CAN_XDIST && safe && launch_is_xdist<T, D, FAM>(p.bbox);

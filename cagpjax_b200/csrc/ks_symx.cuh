@@ -144,7 +144,9 @@ template <int D, int R, int NT, int JC, int MINB, int OPT>
 __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<double> p) {
     constexpr int NW = NT / 32;
     constexpr int NP = SymxCols<D, false>::NP;
-    if (!launch_is_expandable<double, D, RBF>(p.bbox)) return;  // uniform: the general kernel does this launch
+    const int level = launch_expand_level<double, D, RBF>(p.bbox);  // uniform
+    if (level == 0) return;                                          // the general kernel does this launch
+    const bool clamp = level == 2;  // |x|^2 up to 900: u is clamped at 1000 before the exp2 (kernel_math.cuh)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);
     double2* pk = reinterpret_cast<double2*>(tab + kExpTab16Elems);  // [NP][2 JC]
@@ -193,7 +195,8 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<
             __syncthreads();
             symx_stage<D, false, JC, NT>(pk, p.xs, p.ld, p.s, nullptr, j0 + c0, cl, clp, tid);
             __syncthreads();
-            auto pair_step = [&](const double2* __restrict__ slot, double& cacc) {
+            auto pair_step = [&](auto clamp_c, const double2* __restrict__ slot, double& cacc) {
+                constexpr bool CLAMP = decltype(clamp_c)::value;
                 double v[2 * NP];
                 symx_load_col<D, false, JC>(slot, v);
                 if constexpr ((OPT & kSymxOptGroup) != 0) {
@@ -204,6 +207,10 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<
                     for (int t = 0; t < D; ++t)
 #pragma unroll
                         for (int r = 0; r < R; ++r) u[r] = fma(ar[r][t], v[t], u[r]);
+                    if (CLAMP) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) u[r] = fmin(u[r], 1000.0);
+                    }
                     symx_exp2_vec<OPT, R>(u, tab_s, kv);
                     if (!(OPT & kSymxAblNoRow)) {
 #pragma unroll
@@ -217,34 +224,39 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<
                         double u = v[D];  // |b|^2 - 2 a.b
 #pragma unroll
                         for (int t = 0; t < D; ++t) u = fma(ar[r][t], v[t], u);
+                        if (CLAMP) u = fmin(u, 1000.0);
                         const double kv = symx_exp2<OPT>(u, tab_s);  // K' / 2^(-|a|^2)
                         if (!(OPT & kSymxAblNoRow)) racc[r] = fma(kv, v[D + 1], racc[r]);
                         cacc = (OPT & kSymxAblColAdd) ? cacc + kv : fma(kv, srow[r], cacc);
                     }
                 }
             };
-            for (int sub = 0; sub < clp; sub += 32) {
-                const int rem = cl - sub;
-                const double2* __restrict__ gp = pk + 2 * sub;
-                if (rem > kSymTailBroadcast) {
-                    const double2* __restrict__ lp = gp + lane;
-                    double cacc = 0.0;
+            auto sweep = [&](auto clamp_c) {
+                for (int sub = 0; sub < clp; sub += 32) {
+                    const int rem = cl - sub;
+                    const double2* __restrict__ gp = pk + 2 * sub;
+                    if (rem > kSymTailBroadcast) {
+                        const double2* __restrict__ lp = gp + lane;
+                        double cacc = 0.0;
 #pragma unroll SymxUnroll<OPT>::value
-                    for (int t = 0; t < 32; ++t) {
-                        pair_step(lp + t, cacc);
-                        if (!(OPT & kSymxAblNoShfl)) cacc = __shfl_sync(0xffffffffu, cacc, next_lane);
-                    }
-                    colacc[warp * JC + sub + lane] = cacc;
-                } else {
-                    for (int jj = 0; jj < rem; ++jj) {
-                        double cp = 0.0;
-                        pair_step(gp + jj, cp);
+                        for (int t = 0; t < 32; ++t) {
+                            pair_step(clamp_c, lp + t, cacc);
+                            if (!(OPT & kSymxAblNoShfl)) cacc = __shfl_sync(0xffffffffu, cacc, next_lane);
+                        }
+                        colacc[warp * JC + sub + lane] = cacc;
+                    } else {
+                        for (int jj = 0; jj < rem; ++jj) {
+                            double cp = 0.0;
+                            pair_step(clamp_c, gp + jj, cp);
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) cp += __shfl_xor_sync(0xffffffffu, cp, o);
-                        if (lane == 0) colacc[warp * JC + sub + jj] = cp;
+                            for (int o = 16; o > 0; o >>= 1) cp += __shfl_xor_sync(0xffffffffu, cp, o);
+                            if (lane == 0) colacc[warp * JC + sub + jj] = cp;
+                        }
                     }
                 }
-            }
+            };
+            if (clamp) sweep(std::true_type{});
+            else sweep(std::false_type{});
             __syncthreads();
             if (off0 != 0) {  // column sums: Mt[a][j in b]
                 for (int idx = tid; idx < cl; idx += NT) {
@@ -278,7 +290,9 @@ template <int D, int R, int NT, int JC, int MINB, int OPT>
 __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<double> p) {
     constexpr int NW = NT / 32;
     constexpr int NP = SymxCols<D, true>::NP;
-    if (!launch_is_expandable<double, D, RBF>(p.bbox)) return;  // uniform
+    const int level = launch_expand_level<double, D, RBF>(p.bbox);  // uniform, see the forward kernel
+    if (level == 0) return;
+    const bool clamp = level == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);
     double2* pk = reinterpret_cast<double2*>(tab + kExpTab16Elems);  // [NP][2 JC]
@@ -331,8 +345,9 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
             __syncthreads();
             symx_stage<D, true, JC, NT>(pk, p.xs, p.ld, p.s, p.Gt + (int64_t)a * p.ldg, j0 + c0, cl, clp, tid);
             __syncthreads();
-            auto sweep = [&](auto diag_c) {
+            auto sweep = [&](auto diag_c, auto clamp_c) {
                 constexpr bool DIAG = decltype(diag_c)::value;
+                constexpr bool CLAMP = decltype(clamp_c)::value;
                 auto pair_step = [&](const double2* __restrict__ slot, double& cacc) {
                     double v[2 * NP];
                     symx_load_col<D, true, JC>(slot, v);
@@ -344,7 +359,14 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
                         for (int t = 0; t < D; ++t)
 #pragma unroll
                             for (int r = 0; r < R; ++r) u[r] = fma(ar[r][t], v[t], u[r]);
-                        symx_exp2_vec<OPT, R>(u, tab_s, kv);
+                        if (CLAMP) {  // kv from the clamped u; the weight q = |a|^2 + u keeps the true u (kv ~ 0 there)
+                            double uc[R];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) uc[r] = fmin(u[r], 1000.0);
+                            symx_exp2_vec<OPT, R>(uc, tab_s, kv);
+                        } else {
+                            symx_exp2_vec<OPT, R>(u, tab_s, kv);
+                        }
 #pragma unroll
                         for (int r = 0; r < R; ++r) hq[r] = kv[r] * (narow[r] + u[r]);
 #pragma unroll
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
                             double u = v[D];
 #pragma unroll
                             for (int t = 0; t < D; ++t) u = fma(ar[r][t], v[t], u);
-                            const double kv = symx_exp2<OPT>(u, tab_s);
+                            const double kv = symx_exp2<OPT>(CLAMP ? fmin(u, 1000.0) : u, tab_s);
                             const double hq = kv * (narow[r] + u);
                             sacc[r] = fma(kv, v[D + 2], sacc[r]);
                             cacc = fma(kv, grow[r], cacc);
@@ -395,8 +417,13 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
                     }
                 }
             };
-            if (off0 == 0) sweep(std::true_type{});
-            else sweep(std::false_type{});
+            if (clamp) {
+                if (off0 == 0) sweep(std::true_type{}, std::true_type{});
+                else sweep(std::false_type{}, std::true_type{});
+            } else {
+                if (off0 == 0) sweep(std::true_type{}, std::false_type{});
+                else sweep(std::false_type{}, std::false_type{});
+            }
             __syncthreads();
             if (off0 != 0 && !(OPT & kSymxOptNoAtomic)) {
                 for (int idx = tid; idx < cl; idx += NT) {
