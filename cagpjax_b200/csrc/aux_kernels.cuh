@@ -36,11 +36,14 @@ __global__ void __launch_bounds__(1024) bounding_box_kernel(const T* __restrict_
     const int t = blockIdx.x;
     const T* __restrict__ row = xs + (int64_t)t * ld;
     T lo = row[0], hi = row[0];
+    bool bad = false;  // comparisons skip a NaN, so it is tracked separately
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         const T v = row[i];
+        bad |= v != v;
         lo = v < lo ? v : lo;
         hi = v > hi ? v : hi;
     }
+    bad = __syncthreads_or(bad);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const T a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
@@ -54,9 +57,11 @@ __global__ void __launch_bounds__(1024) bounding_box_kernel(const T* __restrict_
             lo = smin[w] < lo ? smin[w] : lo;
             hi = smax[w] > hi ? smax[w] : hi;
         }
-        // a NaN coordinate poisons the box (comparisons with NaN are false): mark it unusable
-        bbox[t] = lo;
-        bbox[dp + t] = hi;
+        // a NaN coordinate poisons the box: every launch_* predicate of kernel_math.cuh compares with '<', which is
+        // false for NaN, so the clamped general kernels run (and propagate the NaN as the reference does)
+        const T qnan = T(nan(""));
+        bbox[t] = bad ? qnan : lo;
+        bbox[dp + t] = bad ? qnan : hi;
     }
 }
 

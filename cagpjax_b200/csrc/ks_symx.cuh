@@ -88,19 +88,22 @@ struct SymxCols {
     static constexpr int NP = (NV + 1) / 2;  // 16-byte packs per column
 };
 
+// Shared-memory layout of a stage: NPF = NV / 2 arrays of 16-byte pairs [2 JC], then - when NV is odd (forward, D odd:
+// the weight s) - one array of 8-byte scalars [2 JC].  A half-filled pair array would be read as LDS.64 with a 16-byte
+// lane stride, a 2-way bank conflict (ncu: 2.65e8 conflicts per c3s forward launch before this split).
 template <int D, bool BWD, int JC>
-__device__ __forceinline__ void symx_load_col(const double2* __restrict__ slot, double (&v)[2 * SymxCols<D, BWD>::NP]) {
-    constexpr int NP = SymxCols<D, BWD>::NP, NV = SymxCols<D, BWD>::NV;
+__device__ __forceinline__ void symx_load_col(const double2* __restrict__ slot, const double* __restrict__ sslot,
+                                              double (&v)[2 * SymxCols<D, BWD>::NP]) {
+    constexpr int NV = SymxCols<D, BWD>::NV, NPF = NV / 2;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) {
-        if (2 * q + 1 < NV) {
-            const double2 t = slot[q * 2 * JC];
-            v[2 * q] = t.x;
-            v[2 * q + 1] = t.y;
-        } else {
-            v[2 * q] = slot[q * 2 * JC].x;
-            v[2 * q + 1] = 0.0;
-        }
+    for (int q = 0; q < NPF; ++q) {
+        const double2 t = slot[q * 2 * JC];
+        v[2 * q] = t.x;
+        v[2 * q + 1] = t.y;
+    }
+    if (NV & 1) {
+        v[NV - 1] = *sslot;  // same slot index in the scalar array
+        v[NV] = 0.0;
     }
 }
 
@@ -109,7 +112,7 @@ template <int D, bool BWD, int JC, int NT>
 __device__ __forceinline__ void symx_stage(double2* __restrict__ pk, const double* __restrict__ xs, int64_t ld,
                                            const double* __restrict__ s, const double* __restrict__ grow_src,
                                            int64_t jbase, int cl, int clp, int tid) {
-    constexpr int NP = SymxCols<D, BWD>::NP, NV = SymxCols<D, BWD>::NV;
+    constexpr int NP = SymxCols<D, BWD>::NP, NV = SymxCols<D, BWD>::NV, NPF = NV / 2;
     for (int idx = tid; idx < clp; idx += NT) {
         const bool in = idx < cl;
         const int64_t j = jbase + (in ? idx : 0);
@@ -127,17 +130,23 @@ __device__ __forceinline__ void symx_stage(double2* __restrict__ pk, const doubl
         if (NV < 2 * NP) v[NV] = 0.0;
         const int slot = ((idx >> 5) << 6) + (idx & 31);
 #pragma unroll
-        for (int q = 0; q < NP; ++q) {
+        for (int q = 0; q < NPF; ++q) {
             const double2 t = make_double2(v[2 * q], v[2 * q + 1]);
             pk[q * 2 * JC + slot] = t;
             pk[q * 2 * JC + slot + 32] = t;
+        }
+        if (NV & 1) {
+            double* sc = reinterpret_cast<double*>(pk + NPF * 2 * JC);
+            sc[slot] = v[NV - 1];
+            sc[slot + 32] = v[NV - 1];
         }
     }
 }
 
 template <int D, bool BWD, int JC, int NT>
 constexpr size_t symx_smem_bytes() {
-    return (size_t)kExpTab16Elems * 8 + (size_t)SymxCols<D, BWD>::NP * 2 * JC * 16 + (size_t)(NT / 32) * JC * 8;
+    constexpr int NV = SymxCols<D, BWD>::NV;
+    return (size_t)kExpTab16Elems * 8 + (size_t)(NV / 2) * 2 * JC * 16 + (size_t)(NV & 1) * 2 * JC * 8 + (size_t)(NT / 32) * JC * 8;
 }
 
 template <int D, int R, int NT, int JC, int MINB, int OPT>
@@ -149,8 +158,9 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<
     const bool clamp = level == 2;  // |x|^2 up to 900: u is clamped at 1000 before the exp2 (kernel_math.cuh)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);
-    double2* pk = reinterpret_cast<double2*>(tab + kExpTab16Elems);  // [NP][2 JC]
-    double* colacc = reinterpret_cast<double*>(pk + NP * 2 * JC);    // [NW][JC]
+    double2* pk = reinterpret_cast<double2*>(tab + kExpTab16Elems);  // [NV / 2][2 JC] pairs, then [NV & 1][2 JC] scalars
+    const double* sc = reinterpret_cast<const double*>(pk + (SymxCols<D, false>::NV / 2) * 2 * JC);
+    double* colacc = reinterpret_cast<double*>(smem_raw + symx_smem_bytes<D, false, JC, NT>() - (size_t)NW * JC * 8);  // [NW][JC]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = exptab16_load(tab, tid, NT);
     const SymTiling& til = p.til;
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<
             auto pair_step = [&](auto clamp_c, const double2* __restrict__ slot, double& cacc) {
                 constexpr bool CLAMP = decltype(clamp_c)::value;
                 double v[2 * NP];
-                symx_load_col<D, false, JC>(slot, v);
+                symx_load_col<D, false, JC>(slot, sc + (slot - pk), v);
                 if constexpr ((OPT & kSymxOptGroup) != 0) {
                     double u[R], kv[R];
 #pragma unroll
@@ -295,8 +305,9 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
     const bool clamp = level == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);
-    double2* pk = reinterpret_cast<double2*>(tab + kExpTab16Elems);  // [NP][2 JC]
-    double* colacc = reinterpret_cast<double*>(pk + NP * 2 * JC);    // [NW][JC]
+    double2* pk = reinterpret_cast<double2*>(tab + kExpTab16Elems);  // [NV / 2][2 JC] pairs, then [NV & 1][2 JC] scalars
+    const double* sc = reinterpret_cast<const double*>(pk + (SymxCols<D, true>::NV / 2) * 2 * JC);
+    double* colacc = reinterpret_cast<double*>(smem_raw + symx_smem_bytes<D, true, JC, NT>() - (size_t)NW * JC * 8);  // [NW][JC]
     __shared__ double red[NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tab_s = exptab16_load(tab, tid, NT);
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
                 constexpr bool CLAMP = decltype(clamp_c)::value;
                 auto pair_step = [&](const double2* __restrict__ slot, double& cacc) {
                     double v[2 * NP];
-                    symx_load_col<D, true, JC>(slot, v);
+                    symx_load_col<D, true, JC>(slot, sc + (slot - pk), v);
                     if constexpr ((OPT & kSymxOptGroup) != 0) {
                         double u[R], kv[R], hq[R];
 #pragma unroll

@@ -310,16 +310,6 @@ def fit(*, model, objective: Callable, train_data: Dataset, optim="adamw", num_i
         raw.append(v.requires_grad_(True))
     if cuda_graph and (callable(optim) or not raw or not all(r.is_cuda for r in raw)):
         raise ValueError("cuda_graph=True needs CUDA training data and one of the built-in optimisers")
-    if cuda_graph and raw[0].dtype == torch.float64 and torch.get_default_dtype() != torch.float64:
-        # capturable Adam keeps its step counter (hence the bias corrections 1 - beta^t) in the DEFAULT dtype;
-        # in float32 that perturbs a float64 trajectory at the 1e-6 level
-        prev = torch.get_default_dtype()
-        torch.set_default_dtype(torch.float64)
-        try:
-            return fit(model=model, objective=objective, train_data=train_data, optim=optim, num_iters=num_iters,
-                       learning_rate=learning_rate, key=key, verbose=verbose, cuda_graph=True)
-        finally:
-            torch.set_default_dtype(prev)
     if callable(optim):
         opt = optim(raw)
     elif optim == "adamw":
@@ -330,6 +320,14 @@ def fit(*, model, objective: Callable, train_data: Dataset, optim="adamw", num_i
         opt = torch.optim.SGD(raw, lr=learning_rate)
     else:
         raise ValueError(f"unknown optimiser {optim!r}")
+    if cuda_graph and optim in ("adam", "adamw"):
+        # capturable Adam would create its step counter (hence the bias corrections 1 - beta^t) in the process-wide
+        # DEFAULT dtype; float32 there perturbs a float64 trajectory at the 1e-6 level.  Create the state here, in the
+        # leaves' own dtype, instead of changing the global default around the fit.
+        for r in raw:
+            opt.state[r] = {"step": torch.zeros((), dtype=r.dtype, device=r.device),
+                            "exp_avg": torch.zeros_like(r, memory_format=torch.preserve_format),
+                            "exp_avg_sq": torch.zeros_like(r, memory_format=torch.preserve_format)}
 
     def install(detach: bool):
         for (owner, attr, leaf), r in zip(leaves, raw):

@@ -198,3 +198,31 @@ def test_symmetric_kernels_stay_inside_their_outputs(family, n, d, k):
     sbr, lbr = N.ks_blocksparse_bwd(family, xs, xs, d, s, k, G, ls)
     assert torch.isfinite(sb).all() and rel_err(sb, sbr) < 1e-11 and rel_err(lb, lbr) < 1e-11
     assert torch.isnan(s_pad[n:]).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_nan_coordinate_poisons_the_bounding_box(dtype):
+    """A NaN input coordinate must not let the launch predicates pick an unclamped fast path from a box computed
+    over the remaining finite points: the box itself becomes NaN (every predicate is then false), the kernels run
+    their general forms and the NaN shows up in the rows / columns it touches, as in the reference (jnp propagates)."""
+    n, d, k = 700, 3, 4
+    g = torch.Generator().manual_seed(2)
+    X = (torch.rand(n, d, generator=g, dtype=torch.float64) * 3).to(dtype).to(DEV)
+    ls = torch.ones(1, dtype=dtype, device=DEV)
+    s = torch.randn(n, generator=g, dtype=torch.float64).to(dtype).to(DEV)
+    xs = N.scale_inputs("rbf", X, ls, X[0])
+    assert torch.isfinite(N.bounding_box(xs)).all()
+    X[123, 1] = float("nan")
+    xs = N.scale_inputs("rbf", X, ls, X[0])
+    bb = N.bounding_box(xs)
+    dp = xs.shape[0]
+    assert torch.isnan(bb[1]) and torch.isnan(bb[dp + 1])
+    assert torch.isfinite(bb[0]) and torch.isfinite(bb[dp]) and torch.isfinite(bb[2]) and torch.isfinite(bb[dp + 2])
+    Mt = N.ks_blocksparse_fwd_sym("rbf", xs, d, s, k, ls, bbox=bb)
+    assert torch.isnan(Mt[:, 123]).all()          # row 123 of M' = K'S: every entry sees the NaN point
+    blk = 123 // (n // k)
+    assert torch.isnan(Mt[blk]).all()             # its own block's column sums over the NaN point
+    other = [b for b in range(k) if b != blk]
+    cols = torch.ones(n, dtype=torch.bool, device=DEV)
+    cols[123] = False
+    assert torch.isfinite(Mt[other][:, cols]).all()
