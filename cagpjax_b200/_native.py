@@ -308,18 +308,21 @@ def sym_zero_rows(family, xs, d, k, lengthscale, bbox) -> int:
     return int(load().cagp_ks_fwd_sym_zero_rows(byref(kd), xs.shape[1], d, k))
 
 
-def sym_fast_path(family, xs, d, k, lengthscale, bbox, backward=False) -> bool:
-    """True if the symmetric call also launches the float64 RBF fast-path kernel (csrc/ks_symx.cuh) AND the bounding
-    box proves its expanded form valid (every scaled |x|^2 < 300), i.e. the fast-path kernel does the work."""
+def sym_fast_path(family, xs, d, k, lengthscale, bbox, backward=False) -> int:
+    """Non-zero if the symmetric call also launches the float64 RBF fast-path kernel (csrc/ks_symx.cuh) AND the
+    bounding box proves its expanded form valid, i.e. the fast-path kernel does the work: 1 = every scaled
+    |x|^2 < 300 (no clamp), 2 = every |x|^2 < 900 (exponent clamp); 0 = the general kernel runs
+    (kernel_math.cuh, launch_expand_level)."""
     if bbox is None:
-        return False
+        return 0
     ls = lengthscale.reshape(-1).to(device=xs.device, dtype=xs.dtype).contiguous()
     kd = make_desc(family, ls, xs.dtype, bbox)
     if not load().cagp_ks_sym_fast_path(byref(kd), xs.shape[1], d, k, 1 if backward else 0):
-        return False
+        return 0
     dp = xs.shape[0]
     m = torch.maximum(bbox[:dp].abs(), bbox[dp:].abs())
-    return bool((m * m).sum() < 300.0)
+    r2 = float((m * m).sum())
+    return 1 if r2 < 300.0 else (2 if r2 < 900.0 else 0)
 
 
 def ks_blocksparse_bwd_sym(family, xs, d, s, k, Gt, lengthscale, a_begin=0, a_end=None, bbox=None):

@@ -71,13 +71,13 @@ __device__ __forceinline__ double symx_exp2(double u, unsigned tab_lane) {
 }
 
 // stage-ordered exp2 of R arguments: kernel_math.cuh (exp2neg16_vec); the ablation flags of OPT are forwarded
-template <int OPT, int R>
+template <int OPT, int R, bool CLAMP>
 __device__ __forceinline__ void symx_exp2_vec(const double (&u)[R], unsigned tab_lane, double (&kv)[R]) {
     if constexpr ((OPT & (kSymxAblNoTable | kSymxAblNoPoly | kSymxOptDadd)) != 0) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) kv[r] = symx_exp2<OPT>(u[r], tab_lane);
+        for (int r = 0; r < R; ++r) kv[r] = symx_exp2<OPT>(CLAMP ? fmin(u[r], 1000.0) : u[r], tab_lane);
     } else {
-        exp2neg16_vec<R>(u, tab_lane, kv);
+        exp2neg16_vec<R, CLAMP>(u, tab_lane, kv);  // CLAMP: integer clamp of the exponent adjustment
     }
 }
 
@@ -217,11 +217,7 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_fwd_kernel(const SymFwdArgs<
                     for (int t = 0; t < D; ++t)
 #pragma unroll
                         for (int r = 0; r < R; ++r) u[r] = fma(ar[r][t], v[t], u[r]);
-                    if (CLAMP) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) u[r] = fmin(u[r], 1000.0);
-                    }
-                    symx_exp2_vec<OPT, R>(u, tab_s, kv);
+                    symx_exp2_vec<OPT, R, CLAMP>(u, tab_s, kv);
                     if (!(OPT & kSymxAblNoRow)) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) racc[r] = fma(kv[r], v[D + 1], racc[r]);
@@ -370,14 +366,8 @@ __global__ void __launch_bounds__(NT, MINB) ks_symx_bwd_kernel(const SymBwdArgs<
                         for (int t = 0; t < D; ++t)
 #pragma unroll
                             for (int r = 0; r < R; ++r) u[r] = fma(ar[r][t], v[t], u[r]);
-                        if (CLAMP) {  // kv from the clamped u; the weight q = |a|^2 + u keeps the true u (kv ~ 0 there)
-                            double uc[R];
-#pragma unroll
-                            for (int r = 0; r < R; ++r) uc[r] = fmin(u[r], 1000.0);
-                            symx_exp2_vec<OPT, R>(uc, tab_s, kv);
-                        } else {
-                            symx_exp2_vec<OPT, R>(u, tab_s, kv);
-                        }
+                        // CLAMP: only kv is clamped; the weight q = |a|^2 + u keeps the true u (kv < 1e-300 there)
+                        symx_exp2_vec<OPT, R, CLAMP>(u, tab_s, kv);
 #pragma unroll
                         for (int r = 0; r < R; ++r) hq[r] = kv[r] * (narow[r] + u[r]);
 #pragma unroll

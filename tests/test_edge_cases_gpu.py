@@ -226,3 +226,31 @@ def test_nan_coordinate_poisons_the_bounding_box(dtype):
     cols = torch.ones(n, dtype=torch.bool, device=DEV)
     cols[123] = False
     assert torch.isfinite(Mt[other][:, cols]).all()
+
+
+@pytest.mark.parametrize("width,level", [(20.0, 1), (36.0, 2), (60.0, 0)])
+def test_expanded_form_levels_against_the_oracle(width, level):
+    """The three range regimes of the float64 RBF symmetric kernels (kernel_math.cuh, launch_expand_level): every
+    scaled |x|^2 < 300 (expanded form, no clamp), < 900 (expanded form, exponent clamp: width 36 has pairs with
+    u = |b|^2 - 2 a.b up to ~2100 > 1000) and beyond (difference form).  Forward against the oracle's dense product,
+    backward against the rectangular general kernel, all three within 1e-11."""
+    n, d, k = 1800, 3, 6
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64) * width
+    x[0], x[1] = torch.zeros(d, dtype=torch.float64), torch.full((d,), width, dtype=torch.float64)  # the two far corners
+    x[n // 2:] = x[: n - n // 2] + 0.2 * torch.randn(n - n // 2, d, generator=g, dtype=torch.float64)  # near pairs
+    x.clamp_(0.0, width)
+    s = torch.randn(n, generator=g, dtype=torch.float64)
+    ls = torch.ones(1, dtype=torch.float64)
+    ref = O.projected_kernel_blocksparse("rbf", x.numpy(), x.numpy(), ls.numpy(), s.numpy(), k)
+    xd, sd, lsd = x.to(DEV), s.to(DEV), ls.to(DEV)
+    xs = N.scale_inputs("rbf", xd, lsd, 0.5 * (xd.amin(0) + xd.amax(0)))
+    bb = N.bounding_box(xs)
+    assert N.sym_fast_path("rbf", xs, d, k, lsd, bb) == level
+    assert N.sym_fast_path("rbf", xs, d, k, lsd, bb, backward=True) == level
+    Mt = N.ks_blocksparse_fwd_sym("rbf", xs, d, sd, k, lsd, bbox=bb)
+    assert torch.isfinite(Mt).all() and rel_err(Mt.T, ref) < 1e-11
+    G = torch.randn(k, n, generator=g, dtype=torch.float64).to(DEV)
+    sb, lb = N.ks_blocksparse_bwd_sym("rbf", xs, d, sd, k, G, lsd, bbox=bb)
+    sbr, lbr = N.ks_blocksparse_bwd("rbf", xs, xs, d, sd, k, G, lsd)
+    assert torch.isfinite(sb).all() and rel_err(sb, sbr) < 1e-11 and rel_err(lb, lbr) < 1e-11
