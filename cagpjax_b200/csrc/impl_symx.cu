@@ -60,7 +60,9 @@ int symx_bwd_variant() { return env_variant("CAGP_SYMX_BWD", 0); }
 
 // The fast path applies to: double, RBF, isotropic, SINGLE shape of the general kernel, D <= 4, a bounding box.
 bool symx_applicable(const cagp_kernel_desc* kd, int64_t n, int k, int dp, bool bwd) {
-    if (kd->dtype != CAGP_F64 || kd->family != CAGP_RBF || kd->n_lengthscale != 1 || !kd->bbox || dp > 4) return false;
+    // the forward sees only the scaled inputs, so ARD lengthscales qualify; the backward's lengthscale cotangent uses
+    // the isotropic identity sum_t (a_t - b_t)^2 = q and needs the per-dimension differences for ARD
+    if (kd->dtype != CAGP_F64 || kd->family != CAGP_RBF || (bwd && kd->n_lengthscale != 1) || !kd->bbox || dp > 4) return false;
     if ((bwd ? symx_bwd_variant() : symx_fwd_variant()) < 0) return false;
     const Shape s = bwd ? bwd_shape(symx_bwd_variant()) : fwd_shape(symx_fwd_variant());
     if (s.rows == 0) return false;

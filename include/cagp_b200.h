@@ -131,7 +131,8 @@ int cagp_ks_blocksparse_fwd_sym_peer(const cagp_kernel_desc* kd, const void* xs,
 
 /* Introspection (host only, no launch): 1 if the symmetric forward (backward != 0: backward) call with this
  * descriptor and shape also launches the float64-RBF fast-path kernel (csrc/ks_symx.cuh), which does the work
- * whenever the bounding box in `kd` proves every scaled |x|^2 < 300 (decided on the device); else 0.  Tests and
+ * whenever the bounding box in `kd` proves every scaled |x|^2 < 900 (decided on the device; below 300 without, above
+ * with an exponent clamp); else 0.  Forward: isotropic or ARD lengthscales; backward: isotropic only.  Tests and
  * bench.py use it to name the kernel instance they exercise. */
 int cagp_ks_sym_fast_path(const cagp_kernel_desc* kd, int64_t n, int32_t d, int32_t k, int32_t backward);
 

@@ -254,3 +254,25 @@ def test_expanded_form_levels_against_the_oracle(width, level):
     sb, lb = N.ks_blocksparse_bwd_sym("rbf", xs, d, sd, k, G, lsd, bbox=bb)
     sbr, lbr = N.ks_blocksparse_bwd("rbf", xs, xs, d, sd, k, G, lsd)
     assert torch.isfinite(sb).all() and rel_err(sb, sbr) < 1e-11 and rel_err(lb, lbr) < 1e-11
+
+
+def test_ard_forward_takes_the_fast_path():
+    """ARD lengthscales only change the input scaling, so the float64 RBF forward runs the expanded-form kernel for
+    them too (the backward needs per-dimension differences and stays on the general kernel); both against the oracle."""
+    n, d, k = 2100, 3, 7
+    g = torch.Generator().manual_seed(23)
+    x = torch.rand(n, d, generator=g, dtype=torch.float64) * 6
+    s = torch.randn(n, generator=g, dtype=torch.float64)
+    ls = torch.tensor([0.7, 1.3, 2.1], dtype=torch.float64)
+    ref = O.projected_kernel_blocksparse("rbf", x.numpy(), x.numpy(), ls.numpy(), s.numpy(), k)
+    xd, sd, lsd = x.to(DEV), s.to(DEV), ls.to(DEV)
+    xs = N.scale_inputs("rbf", xd, lsd, 0.5 * (xd.amin(0) + xd.amax(0)))
+    bb = N.bounding_box(xs)
+    assert N.sym_fast_path("rbf", xs, d, k, lsd, bb) == 1
+    assert N.sym_fast_path("rbf", xs, d, k, lsd, bb, backward=True) == 0
+    Mt = N.ks_blocksparse_fwd_sym("rbf", xs, d, sd, k, lsd, bbox=bb)
+    assert rel_err(Mt.T, ref) < 1e-12
+    G = torch.randn(k, n, generator=g, dtype=torch.float64).to(DEV)
+    sb, lb = N.ks_blocksparse_bwd_sym("rbf", xs, d, sd, k, G, lsd, bbox=bb)
+    sbr, lbr = N.ks_blocksparse_bwd("rbf", xs, xs, d, sd, k, G, lsd)
+    assert lb.numel() == d and rel_err(sb, sbr) < 1e-11 and rel_err(lb, lbr) < 1e-11
