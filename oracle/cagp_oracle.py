@@ -17,8 +17,10 @@ tests hold no golden vectors (every assertion is relational).  The kernel formul
 from GPJax (``gpjax>=0.14.0rc1``, not vendored in /root/reference) and are restated from
 its published definitions.  What pins this oracle instead: the relational identities the
 reference's own tests assert (tests/test_oracle.py re-expresses them), a textbook exact-GP
-cross-check at k = n, finite differences for every gradient, and agreement of the two
-independent formulations below (literal vs structured).
+cross-check at k = n, finite differences for every gradient, agreement of the two
+independent formulations below (literal vs structured), and a third-party anchor
+(tests/test_oracle_third_party_anchors.py): scikit-learn's kernels and exact GP regression
+reproduce the kernel formulas (1e-13) and the k = n posterior / ELBO (1e-9) of this file.
 
 Reference citations are relative to /root/reference/src/cagpjax unless noted.
 """
