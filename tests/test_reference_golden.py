@@ -1,0 +1,128 @@
+"""The oracle against golden vectors produced by the REFERENCE'S OWN SOURCE (CPU).
+
+`tests/golden/reference_golden.npz` was written by `tests/golden/make_reference_golden.py`, which imports the unmodified
+`/root/reference/src/cagpjax` under numpy stand-ins for its absent dependencies (oracle/refshim/README.md says what
+that pins: the cagpjax package's own logic; not jax / CoLA / GPJax themselves).  Here:
+
+  * every quantity the reference computed (init, ELBO, KL, variational expectation, predictive mean / variance /
+    covariance at train and test inputs, log_prob) is compared with the oracle's restatement at 1e-12;
+  * the oracle's reverse-mode gradients are compared with central finite differences OF THE REFERENCE (1e-6: the
+    differences are the limit, not the oracle);
+  * when the reference sources are present (this container; not the GPU box) the generator is re-run in a fresh
+    process and must reproduce the committed fixture, so the fixture provably is the script's output.
+"""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cagp_oracle as O
+from oracle import cagp_oracle_ext as OX
+from oracle.run_reference import reference_available
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "reference_golden.npz")
+G = np.load(GOLDEN)
+CASES = [str(c) for c in G["case_names"]]
+
+
+def case(name):
+    pre = name + "/"
+    return {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+
+
+def t(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float64))
+
+
+def close(a, b, tol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b)))
+
+
+BLOCKSPARSE_CHOL = [c for c in CASES if str(G[c + "/actions_kind"]) == "blocksparse" and str(G[c + "/solver"]) == "cholesky"]
+DENSE = [c for c in CASES if str(G[c + "/actions_kind"]) == "dense"]
+PINV = [c for c in CASES if str(G[c + "/solver"]) == "pseudoinverse"]
+
+
+def test_fixture_covers_the_path():
+    fams = {str(G[c + "/family"]) for c in CASES}
+    assert fams == {"rbf", "matern12", "matern32", "matern52"}
+    assert BLOCKSPARSE_CHOL and DENSE and PINV
+    assert any(int(G[c + "/x"].shape[0]) % int(G[c + "/n_actions"]) for c in BLOCKSPARSE_CHOL)      # an overhang block
+    assert any(G[c + "/hp_lengthscale"].ndim == 1 for c in CASES)                                    # ARD
+
+
+@pytest.mark.parametrize("name", BLOCKSPARSE_CHOL)
+def test_oracle_matches_reference_blocksparse(name):
+    c = case(name)
+    fam, k = str(c["family"]), int(c["n_actions"])
+    p = O.make_params(c["hp_lengthscale"], c["hp_variance"], c["hp_obs_stddev"], c["hp_mean_constant"], c["actions"])
+    x, y, z = t(c["x"]), t(c["y"]), t(c["z"])
+    st = O.cagp_init(fam, x, y, p, k, batch_size=7)
+    assert close(st.S.numpy(), c["actions_dense"], 1e-15)
+    assert close(st.residual_proj.numpy(), c["residual_proj"], 1e-13)
+    assert close(st.repr_weights_proj.numpy(), c["repr_weights_proj"], 1e-10)  # a solve: conditioned by cov_prior_proj
+    assert close(torch.diag(st.obs_cov_proj).numpy() if st.obs_cov_proj.dim() == 1 else st.obs_cov_proj.numpy(), c["obs_cov_proj"], 1e-14)
+    assert close(st.L.numpy(), c["cov_prior_proj_chol"], 1e-12)
+    assert close(float(O.cagp_elbo(fam, st, p)), float(c["elbo"]), 1e-12)
+    assert close(float(O.cagp_prior_kl(st)), float(c["prior_kl"]), 1e-11)
+    assert close(O.cagp_variational_expectation(fam, st, p).numpy(), c["variational_expectation"], 1e-12)
+    m, v = O.cagp_predict(fam, st, p)
+    assert close(m.numpy(), c["train_mean"], 1e-12) and close(v.numpy(), c["train_variance"], 1e-12)
+    m, v, cov = O.cagp_predict(fam, st, p, z, full_cov=True)
+    assert close(m.numpy(), c["test_mean"], 1e-12) and close(v.numpy(), c["test_variance"], 1e-12)
+    assert close(cov.numpy(), c["test_covariance"], 1e-12)
+    # structured (independent) formulation of the oracle against the reference's ELBO as well
+    es = O.elbo_structured(fam, c["x"], c["y"], c["hp_lengthscale"], float(c["hp_variance"]), float(c["hp_obs_stddev"]),
+                           float(c["hp_mean_constant"]), c["actions"], k)
+    assert close(float(es), float(c["elbo"]), 1e-11)
+
+
+@pytest.mark.parametrize("name", BLOCKSPARSE_CHOL)
+def test_oracle_gradients_match_reference_finite_differences(name):
+    c = case(name)
+    fam, k = str(c["family"]), int(c["n_actions"])
+    p = O.make_params(c["hp_lengthscale"], c["hp_variance"], c["hp_obs_stddev"], c["hp_mean_constant"], c["actions"])
+    val, grads = O.elbo_and_grad_literal(fam, t(c["x"]), t(c["y"]), p, k)
+    assert close(float(val), float(c["elbo"]), 1e-12)
+    for leaf in ("lengthscale", "variance", "obs_stddev", "mean_constant", "actions"):
+        ref = np.asarray(c["grad_" + leaf], dtype=np.float64)
+        got = grads[leaf].numpy().reshape(ref.shape)
+        assert np.max(np.abs(got - ref)) <= 1e-6 * max(1.0, np.max(np.abs(ref))), leaf
+
+
+@pytest.mark.parametrize("name", DENSE + PINV)
+def test_oracle_matches_reference_dense_actions_and_pseudoinverse(name):
+    c = case(name)
+    fam = str(c["family"])
+    solver = "pinv" if str(c["solver"]) == "pseudoinverse" else "cholesky"
+    S = t(c["actions_dense"])
+    args = (fam, t(c["x"]), t(c["y"]), t(c["hp_lengthscale"]), t(c["hp_variance"]), t(c["hp_obs_stddev"]), t(c["hp_mean_constant"]), S)
+    elbo, m, v = OX.elbo_dense_actions(*args, solver=solver)
+    assert close(float(elbo), float(c["elbo"]), 1e-10)
+    assert close(m.numpy(), c["train_mean"], 1e-10) and close(v.numpy(), c["train_variance"], 1e-10)
+    elbo, m, v = OX.elbo_dense_actions(*args, solver=solver, z=t(c["z"]))
+    assert close(m.numpy(), c["test_mean"], 1e-10) and close(v.numpy(), c["test_variance"], 1e-10)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference sources are not on this machine")
+def test_fixture_is_what_the_generator_writes(tmp_path):
+    out = str(tmp_path / "regen.npz")
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), out], check=True, env=env,
+                   capture_output=True, timeout=600)
+    R = np.load(out)
+    assert sorted(R.files) == sorted(G.files)
+    for key in G.files:
+        a, b = G[key], R[key]
+        if a.dtype.kind in "US":
+            assert np.array_equal(a, b), key
+        elif key.split("/")[-1].startswith("grad_"):
+            assert np.allclose(a, b, rtol=0, atol=2e-6 * max(1.0, np.max(np.abs(a)))), key   # differences of ~1e-16-noisy ELBOs / 2e-5
+        else:
+            assert np.allclose(a, b, rtol=1e-11, atol=1e-12), key

@@ -1,0 +1,91 @@
+"""The CUDA path against golden vectors produced by the REFERENCE'S OWN SOURCE.
+
+`tests/golden/reference_golden.npz` holds inputs and the outputs of the unmodified reference package for them (made by
+`tests/golden/make_reference_golden.py`; what that pins: oracle/refshim/README.md).  The fixture travels to the GPU box,
+the reference does not.  Float64, tolerance 1e-10 (north star) on values; the reference's gradients are central finite
+differences of its own ELBO, so gradient agreement is asserted at 1e-6 (the differences are the limit)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cagpjax_b200 as cagp
+from cagpjax_b200 import gpx
+from cagpjax_b200.policies import DensePolicy
+from cagpjax_b200.solvers import PseudoInverse
+from tests.util import KERNELS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+CASES = [str(c) for c in G["case_names"]]
+
+
+def case(name):
+    pre = name + "/"
+    return {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+
+
+def dev(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float64)).to(DEV)
+
+
+def err(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a.reshape(b.shape) - b)) / max(1.0, np.max(np.abs(b))))
+
+
+def build(c):
+    fam, k = str(c["family"]), int(c["n_actions"])
+    kernel = KERNELS[fam](lengthscale=dev(c["hp_lengthscale"]), variance=dev(c["hp_variance"]),
+                          compute_engine=cagp.computations.LazyKernelComputation())
+    prior = gpx.Prior(kernel=kernel, mean_function=gpx.Constant(dev(c["hp_mean_constant"])))
+    lik = gpx.Gaussian(int(c["x"].shape[0]), obs_stddev=dev(c["hp_obs_stddev"]))
+    if str(c["actions_kind"]) == "blocksparse":
+        policy = cagp.BlockSparsePolicy(n_actions=k, nz_values=dev(c["actions"]))
+    else:
+        policy = DensePolicy(dev(c["actions"]))
+    kw = {"solver": PseudoInverse()} if str(c["solver"]) == "pseudoinverse" else {}
+    model = cagp.ComputationAwareGP(prior * lik, policy, **kw)
+    data = gpx.Dataset(dev(c["x"]), dev(c["y"]).reshape(-1, 1))
+    return model, data
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_values_match_the_reference(name):
+    c = case(name)
+    model, data = build(c)
+    tol = 1e-10 if str(c["solver"]) == "cholesky" else 1e-9   # the pseudo-inverse route goes through an eigendecomposition
+    with torch.no_grad():
+        st = model.init(data)
+        assert err(st.residual_proj, c["residual_proj"]) < tol
+        assert err(st.repr_weights_proj, c["repr_weights_proj"]) < 1e-8   # a solve, conditioned by S^T K^ S
+        assert err(model.elbo(st), c["elbo"]) < tol
+        assert err(model.prior_kl(st), c["prior_kl"]) < tol * 10
+        assert err(model.variational_expectation(st), c["variational_expectation"]) < tol
+        q = model.predict(st)
+        assert err(q.mean, c["train_mean"]) < tol and err(q.variance, c["train_variance"]) < tol
+        q = model.predict(st, dev(c["z"]))
+        assert err(q.mean, c["test_mean"]) < tol and err(q.variance, c["test_variance"]) < tol
+        assert err(q.scale.to_dense(), c["test_covariance"]) < tol
+        if str(c["solver"]) == "cholesky":
+            assert err(q.log_prob(q.mean + 0.05), c["test_log_prob_of_mean_plus"]) < 1e-8
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if str(G[n + "/solver"]) == "cholesky"])
+def test_gradients_match_finite_differences_of_the_reference(name):
+    c = case(name)
+    model, data = build(c)
+    val, grads = gpx.value_and_grad(lambda m, d: m.elbo(m.init(d)), model, data)
+    assert err(val, c["elbo"]) < 1e-10
+    names = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev", "constant": "mean_constant",
+             "nz_values": "actions", "actions": "actions"}
+    seen = 0
+    for key, g in grads.items():
+        leaf = names[key.split(".")[1]]
+        assert err(g, c["grad_" + leaf]) < 1e-6, key
+        seen += 1
+    assert seen == 5
