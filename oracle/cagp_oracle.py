@@ -11,16 +11,17 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this module - always as the checker or the timed
 CPU baseline, never as part of the shipped product path.
 
-PARITY UNPINNED: the reference cannot be imported here or on the GPU box (jax, jaxlib,
-gpjax, cola-ml, lineax, equinox, paramax are absent and there is no network), and its
-tests hold no golden vectors (every assertion is relational).  The kernel formulas come
-from GPJax (``gpjax>=0.14.0rc1``, not vendored in /root/reference) and are restated from
-its published definitions.  What pins this oracle instead: the relational identities the
-reference's own tests assert (tests/test_oracle.py re-expresses them), a textbook exact-GP
-cross-check at k = n, finite differences for every gradient, agreement of the two
-independent formulations below (literal vs structured), and a third-party anchor
-(tests/test_oracle_third_party_anchors.py): scikit-learn's kernels and exact GP regression
-reproduce the kernel formulas (1e-13) and the k = n posterior / ELBO (1e-9) of this file.
+PARITY: the reference cannot be imported here as is (jax, jaxlib, gpjax, cola-ml, lineax, equinox,
+paramax are absent and there is no network), and its tests hold no golden vectors (every
+assertion is relational).  Since round 2 its UNMODIFIED SOURCE is executed under numpy stand-ins
+for those dependencies (oracle/refshim, oracle/run_reference.py) and this oracle is pinned against
+what it computes: tests/golden/reference_golden.npz (generator tests/golden/make_reference_golden.py),
+checked in tests/test_reference_golden.py at 1e-12.  NOT pinned: the third-party packages
+themselves - the GPJax kernel formulas (``gpjax>=0.14.0rc1``, not vendored in /root/reference) are
+restated from their published definitions in both the stand-ins and this file; they are anchored on
+scikit-learn's kernels and exact GP regression (tests/test_oracle_third_party_anchors.py).  Further
+pins: the relational identities the reference's own tests assert (tests/test_oracle.py), finite
+differences for every gradient, and agreement of the two independent formulations below.
 
 Reference citations are relative to /root/reference/src/cagpjax unless noted.
 """

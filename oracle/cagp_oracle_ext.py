@@ -10,10 +10,14 @@ Restates, in plain torch float64 on the CPU (scalar / column loops, no shared co
 
 Only ``tests/`` may import this module.
 
-PARITY UNPINNED: same situation as ``cagp_oracle.py`` - the reference (and matfree, which owns the Lanczos
-recurrence) cannot be imported here and the reference's tests hold no golden vectors for these rows.  Pins used
-instead: the relational identities of tests/test_solvers.py, tests/test_linalg.py and tests/test_policies.py of
-the reference (re-expressed in tests/test_oracle_ext.py), dense ``eigh`` / ``lstsq`` cross-checks and finite
+PARITY: same situation as ``cagp_oracle.py`` - the reference cannot be imported here as is; since round 2 its
+unmodified source runs under the numpy stand-ins of oracle/refshim and this file is pinned against what it computes
+(tests/golden/reference_golden_ext.npz from tests/golden/make_reference_golden_ext.py, checked in
+tests/test_reference_golden.py): ``orthogonalize`` (QR / CGS / MGS), pseudo-input actions, and the dense-action model
+chain with either solver.  NOT pinned: the Lanczos recurrence (owned by matfree, not vendored) and the third-party
+packages themselves.  Further pins: the relational identities of tests/test_solvers.py, tests/test_linalg.py and
+tests/test_policies.py of the reference (re-expressed in tests/test_oracle_ext.py), dense ``eigh`` / ``lstsq``
+cross-checks and finite
 differences.  Reference citations are relative to /root/reference/src/cagpjax.
 """
 

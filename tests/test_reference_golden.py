@@ -126,3 +126,73 @@ def test_fixture_is_what_the_generator_writes(tmp_path):
             assert np.allclose(a, b, rtol=0, atol=2e-6 * max(1.0, np.max(np.abs(a)))), key   # differences of ~1e-16-noisy ELBOs / 2e-5
         else:
             assert np.allclose(a, b, rtol=1e-11, atol=1e-12), key
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# widened rows: tests/golden/reference_golden_ext.npz from tests/golden/make_reference_golden_ext.py
+# ------------------------------------------------------------------------------------------------------------------
+GX = np.load(os.path.join(HERE, "golden", "reference_golden_ext.npz"))
+ORTH = {"qr": OX.orthogonalize_qr, "cgs": OX.orthogonalize_cgs, "mgs": OX.orthogonalize_mgs}
+
+
+@pytest.mark.parametrize("matrix", ["full", "deficient", "ill"])
+@pytest.mark.parametrize("method", ["qr", "cgs", "mgs"])
+@pytest.mark.parametrize("n_reortho", [0, 1])
+def test_oracle_orthogonalize_matches_reference(matrix, method, n_reortho):
+    A = t(GX[f"orth/{matrix}/A"])
+    ref = GX[f"orth/{matrix}/{method}/{n_reortho}"]
+    got = ORTH[method](A, n_reortho).numpy()
+    if matrix == "deficient" and method in ("qr", "mgs"):
+        # rank-deficient input: QR and MGS (rtol = 0) normalise the rounding noise left in the dependent column (4) to
+        # unit length, and column 5 is orthogonalised against that arbitrary direction; columns 0-3 are well defined
+        # (CGS zeroes the dependent column through its rtol and is compared in full below)
+        assert close(got[:, :4], ref[:, :4], 1e-11)
+        if method == "qr":
+            assert close(got.T @ got, np.eye(6), 1e-12) and close(ref.T @ ref, np.eye(6), 1e-12)
+    else:
+        tol = 1e-6 if matrix == "ill" else 1e-11   # ill-conditioned input amplifies last-bit differences of the sums
+        assert close(got, ref, tol)
+    assert bool(GX["orth/operator_qr_is_stiefel"]) and bool(GX["orth/stiefel_passes_through"])
+
+
+def test_reference_eigh_is_a_spectral_decomposition():
+    B = GX["eigh/A"]
+    w, V = np.linalg.eigh(B)
+    assert close(w, GX["eigh/eigenvalues"], 1e-12)
+    assert close(V[:, :3] @ V[:, :3].T, GX["eigh/projector_first3"], 1e-10)
+    assert bool(GX["eigh/is_unitary"])
+
+
+@pytest.mark.parametrize("name", [str(c) for c in GX["model_case_names"]])
+def test_oracle_matches_reference_pseudo_input_models(name):
+    pre = name + "/"
+    c = {k[len(pre):]: GX[k] for k in GX.files if k.startswith(pre)}
+    fam = str(c["family"])
+    S_raw = OX.pseudo_input_actions(fam, t(c["x"]), t(c["pseudo_inputs"]), t(c["hp_lengthscale"]), t(c["hp_variance"]))
+    assert close(S_raw.numpy(), c["actions_raw"], 1e-13)
+    meth = str(c["method"])
+    S = S_raw if meth == "none" else ORTH[meth](S_raw, int(c["n_reortho"]))
+    assert close(S.numpy(), c["actions"], 1e-9)
+    solver = "pinv" if str(c["solver"]) == "pseudoinverse" else "cholesky"
+    args = (fam, t(c["x"]), t(c["y"]), t(c["hp_lengthscale"]), t(c["hp_variance"]), t(c["hp_obs_stddev"]), t(c["hp_mean_constant"]), S)
+    elbo, m, v = OX.elbo_dense_actions(*args, solver=solver)
+    tol = 1e-9 if meth != "none" else 1e-6   # raw pseudo-input actions: S^T K^ S is ill-conditioned (cond ~ 1e9), see DESIGN 3b
+    assert close(float(elbo), float(c["elbo"]), tol)
+    assert close(m.numpy(), c["train_mean"], tol) and close(v.numpy(), c["train_variance"], tol)
+    elbo, m, v = OX.elbo_dense_actions(*args, solver=solver, z=t(c["z"]))
+    assert close(m.numpy(), c["test_mean"], tol) and close(v.numpy(), c["test_variance"], tol)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference sources are not on this machine")
+def test_ext_fixture_is_what_the_generator_writes(tmp_path):
+    out = str(tmp_path / "regen_ext.npz")
+    subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden_ext.py"), out], check=True,
+                   capture_output=True, timeout=600)
+    R = np.load(out)
+    assert sorted(R.files) == sorted(GX.files)
+    for key in GX.files:
+        a, b = GX[key], R[key]
+        if a.dtype.kind in "USb":
+            assert np.array_equal(a, b), key
+        else:
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-11), key

@@ -89,3 +89,43 @@ def test_gradients_match_finite_differences_of_the_reference(name):
         assert err(g, c["grad_" + leaf]) < 1e-6, key
         seen += 1
     assert seen == 5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# widened rows: pseudo-input actions, orthogonalisation policies, both solvers
+# (tests/golden/reference_golden_ext.npz from tests/golden/make_reference_golden_ext.py)
+# ------------------------------------------------------------------------------------------------------------------
+GX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_ext.npz"))
+
+
+@pytest.mark.parametrize("name", [str(c) for c in GX["model_case_names"]])
+def test_pseudo_input_models_match_the_reference(name):
+    from cagpjax_b200.linalg import OrthogonalizationMethod
+    from cagpjax_b200.policies import OrthogonalizationPolicy, PseudoInputPolicy
+
+    pre = name + "/"
+    c = {k[len(pre):]: GX[k] for k in GX.files if k.startswith(pre)}
+    fam, meth = str(c["family"]), str(c["method"])
+    kernel = KERNELS[fam](lengthscale=dev(c["hp_lengthscale"]), variance=dev(c["hp_variance"]),
+                          compute_engine=cagp.computations.LazyKernelComputation())
+    prior = gpx.Prior(kernel=kernel, mean_function=gpx.Constant(dev(c["hp_mean_constant"])))
+    lik = gpx.Gaussian(int(c["x"].shape[0]), obs_stddev=dev(c["hp_obs_stddev"]))
+    data = gpx.Dataset(dev(c["x"]), dev(c["y"]).reshape(-1, 1))
+    policy = PseudoInputPolicy(dev(c["pseudo_inputs"]), data, kernel)
+    with torch.no_grad():
+        assert err(policy.to_actions(None).to_dense(), c["actions_raw"]) < 1e-12
+    if meth != "none":
+        policy = OrthogonalizationPolicy(policy, method=OrthogonalizationMethod(meth), n_reortho=int(c["n_reortho"]))
+    kw = {"solver": PseudoInverse()} if str(c["solver"]) == "pseudoinverse" else {}
+    model = cagp.ComputationAwareGP(prior * lik, policy, **kw)
+    # raw pseudo-input actions: S^T K^ S has condition number ~1e9, every solve loses that many digits
+    tol = 1e-8 if meth != "none" else 1e-5
+    with torch.no_grad():
+        st = model.init(data)
+        if meth != "none":
+            assert err(st.actions.to_dense(), c["actions"]) < 1e-8
+        assert err(model.elbo(st), c["elbo"]) < tol
+        q = model.predict(st)
+        assert err(q.mean, c["train_mean"]) < tol and err(q.variance, c["train_variance"]) < tol
+        q = model.predict(st, dev(c["z"]))
+        assert err(q.mean, c["test_mean"]) < tol and err(q.variance, c["test_variance"]) < tol
