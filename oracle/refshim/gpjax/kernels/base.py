@@ -8,8 +8,8 @@ class AbstractKernel:
     name = "AbstractKernel"
 
     def __init__(self, active_dims=None, lengthscale=1.0, variance=1.0, n_dims=None, compute_engine=None):
-        self.lengthscale = lengthscale if isinstance(lengthscale, Parameter) else PositiveReal(np.asarray(lengthscale, dtype=np.float64))
-        self.variance = variance if isinstance(variance, Parameter) else NonNegativeReal(np.asarray(variance, dtype=np.float64))
+        self.lengthscale = lengthscale if isinstance(lengthscale, Parameter) else PositiveReal(np.asarray(lengthscale))
+        self.variance = variance if isinstance(variance, Parameter) else NonNegativeReal(np.asarray(variance))
         self.compute_engine = compute_engine if compute_engine is not None else DenseKernelComputation()
 
     def gram(self, x):

@@ -6,7 +6,7 @@ from .parameters import NonNegativeReal, Parameter, _value
 class Gaussian:
     def __init__(self, num_datapoints, obs_stddev=1.0):
         self.num_datapoints = num_datapoints
-        self.obs_stddev = obs_stddev if isinstance(obs_stddev, Parameter) else NonNegativeReal(np.asarray(obs_stddev, dtype=np.float64))
+        self.obs_stddev = obs_stddev if isinstance(obs_stddev, Parameter) else NonNegativeReal(np.asarray(obs_stddev))
 
     def expected_log_likelihood(self, y, mean, variance):
         """E_q[log N(y | f, sigma^2)] for q(f) = N(mean, variance), summed over the output axis (GPJax likelihoods.py)."""

@@ -10,7 +10,7 @@ class AbstractMeanFunction:
 
 class Constant(AbstractMeanFunction):
     def __init__(self, constant=0.0):
-        self.constant = constant if isinstance(constant, Parameter) else Real(np.asarray(constant, dtype=np.float64))
+        self.constant = constant if isinstance(constant, Parameter) else Real(np.asarray(constant))
 
     def __call__(self, x):
         c = _value(self.constant)

@@ -65,16 +65,47 @@ def _wrap(x):
 def _forward(fn):
     def call(*a, **k):
         k.pop("precision", None)
-        return _wrap(fn(*a, **k))
+        out = fn(*a, **k)
+        # jax: functions of Python scalars give WEAKLY typed results (they do not promote float32 operands later)
+        if isinstance(out, _np.floating) and a and all(isinstance(x, (int, float)) and not isinstance(x, _np.generic) for x in a):
+            return _WeakFloat(out)
+        return _wrap(out)
 
     call.__name__ = getattr(fn, "__name__", "fn")
     return call
+
+
+class _WeakFloat(float):
+    """Result of a jnp function applied to Python scalars: weakly typed (a Python float to numpy's promotion rules),
+    with the array methods the reference calls on it."""
+
+    def astype(self, dtype):
+        return _np.asarray(float(self), dtype=dtype)[()]
+
+    @property
+    def dtype(self):
+        return _np.dtype(_np.float64)
+
+    ndim = 0
+    shape = ()
 
 
 class _Linalg:
     def __getattr__(self, name):
         obj = getattr(_linalg, name)
         return _forward(obj) if callable(obj) and not isinstance(obj, type) else obj
+
+    @staticmethod
+    def lstsq(a, b, rcond=None):
+        """jnp.linalg.lstsq: SVD solution with rcond = eps(dtype) * max(m, n) by default."""
+        a, b = _np.asarray(a), _np.asarray(b)
+        u, s, vt = _linalg.svd(a, full_matrices=False)
+        if rcond is None:
+            rcond = _np.finfo(a.dtype).eps * max(a.shape)
+        keep = s > rcond * s[0]
+        sinv = _np.where(keep, 1.0 / _np.where(keep, s, 1), 0).astype(a.dtype)
+        x = vt.T @ (sinv[:, None] * (u.T @ b) if b.ndim == 2 else sinv * (u.T @ b))
+        return _wrap(x), None, int(keep.sum()), _wrap(s)
 
     @staticmethod
     def eigh(a, UPLO=None, symmetrize_input=True):

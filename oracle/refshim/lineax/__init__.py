@@ -15,6 +15,15 @@ class AbstractLinearOperator:
     def T(self):
         return self.transpose()
 
+    def in_size(self):
+        return self.as_matrix().shape[1]
+
+    def out_size(self):
+        return self.as_matrix().shape[0]
+
+    def __add__(self, other):
+        return AddLinearOperator(self, other)
+
 
 class _Tag:
     def __init__(self, name):
@@ -85,6 +94,20 @@ class IdentityLinearOperator(AbstractLinearOperator):
 
     def transpose(self):
         return self
+
+
+class AddLinearOperator(AbstractLinearOperator):
+    def __init__(self, operator1, operator2):
+        self.operator1, self.operator2 = operator1, operator2
+
+    def mv(self, vector):
+        return self.operator1.mv(vector) + self.operator2.mv(vector)
+
+    def as_matrix(self):
+        return self.operator1.as_matrix() + self.operator2.as_matrix()
+
+    def transpose(self):
+        return AddLinearOperator(self.operator1.transpose(), self.operator2.transpose())
 
 
 @functools.singledispatch

@@ -1,2 +1,2 @@
 from . import constraints, distribution  # noqa: F401
-from .distribution import Distribution  # noqa: F401
+from .distribution import Distribution, MultivariateNormal  # noqa: F401
