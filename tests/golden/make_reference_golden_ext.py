@@ -58,6 +58,39 @@ def main():
     out["eigh/projector_first3"] = V[:, :3] @ V[:, :3].T   # sign-invariant
     out["eigh/is_unitary"] = np.array(res.eigenvectors.isa(cola.Unitary))
 
+    # --- operators of the hot path: BlockDiagonalSparse, block normalisation, sparse x diagonal congruence, LazyKernel
+    from cagpjax.linalg import congruence_transform
+    from cagpjax.operators import BlockDiagonalSparse, LazyKernel
+    from cagpjax.policies.block_sparse import _normalize_by_blocks
+
+    for tag, n, k in (("overhang", 23, 5), ("even", 24, 6), ("single", 9, 1), ("per_point", 7, 7)):
+        vals = rng.normal(size=n)
+        op = BlockDiagonalSparse(vals, k)
+        X = rng.normal(size=(k, 3))
+        Y = rng.normal(size=(4, n))
+        dvec = rng.uniform(0.5, 2.0, size=n)
+        out[f"bds/{tag}/nz_values"] = vals
+        out[f"bds/{tag}/n_blocks"] = np.int64(k)
+        out[f"bds/{tag}/X"], out[f"bds/{tag}/Y"], out[f"bds/{tag}/dvec"] = X, Y, dvec
+        out[f"bds/{tag}/matmat"] = np.asarray(op @ X)
+        out[f"bds/{tag}/rmatmat"] = np.asarray(Y @ op)
+        out[f"bds/{tag}/T_matmat"] = np.asarray(op.T @ Y.T)
+        out[f"bds/{tag}/dense"] = np.asarray(op.to_dense())
+        out[f"bds/{tag}/normalized"] = np.asarray(_normalize_by_blocks(vals, k))
+        out[f"bds/{tag}/congruence_diag"] = np.asarray(congruence_transform(op, cola.ops.Diagonal(dvec)).diag)
+        out[f"bds/{tag}/congruence_scalar"] = np.asarray(congruence_transform(op, cola.ops.ScalarMul(0.37, (n, n), np.float64)).diag)
+    for fam in ("rbf", "matern12", "matern32", "matern52"):
+        K = {"rbf": gpjax.kernels.RBF, "matern12": gpjax.kernels.Matern12, "matern32": gpjax.kernels.Matern32,
+             "matern52": gpjax.kernels.Matern52}[fam](lengthscale=np.array([0.8, 1.7, 1.1]), variance=np.float64(1.4))
+        x1, x2 = rng.uniform(-2, 2, size=(19, 3)), rng.uniform(-2, 2, size=(26, 3))
+        R, Lm = rng.normal(size=(26, 4)), rng.normal(size=(3, 19))
+        lk = LazyKernel(K, x1, x2, batch_size=6)
+        out[f"lazy/{fam}/x1"], out[f"lazy/{fam}/x2"], out[f"lazy/{fam}/R"], out[f"lazy/{fam}/L"] = x1, x2, R, Lm
+        out[f"lazy/{fam}/matmat"] = np.asarray(lk @ R)
+        out[f"lazy/{fam}/rmatmat"] = np.asarray(Lm @ lk)
+        out[f"lazy/{fam}/dense"] = np.asarray(lk.to_dense())
+        out[f"lazy/{fam}/batch_rows_1GB"] = np.int64(LazyKernel(K, x1, x2).batch_size_row)
+
     # --- pseudo-input actions and the models built on them
     kernels = {"rbf": gpjax.kernels.RBF, "matern32": gpjax.kernels.Matern32, "matern52": gpjax.kernels.Matern52}
     cases = [("pi_rbf_qr_chol", "rbf", 42, 2, 6, "qr", 0, "cholesky"), ("pi_m32_mgs_chol", "matern32", 36, 3, 5, "mgs", 1, "cholesky"),

@@ -196,3 +196,50 @@ def test_ext_fixture_is_what_the_generator_writes(tmp_path):
             assert np.array_equal(a, b), key
         else:
             assert np.allclose(a, b, rtol=1e-9, atol=1e-11), key
+
+
+@pytest.mark.parametrize("tag", ["overhang", "even", "single", "per_point"])
+def test_oracle_block_operators_match_reference(tag):
+    g = lambda k: GX[f"bds/{tag}/{k}"]
+    vals, k = t(g("nz_values")), int(g("n_blocks"))
+    assert close(O.bds_matmat(vals, k, t(g("X"))).numpy(), g("matmat"), 1e-15)
+    assert close(O.bds_rmatmat(vals, k, t(g("Y"))).numpy(), g("rmatmat"), 1e-14)
+    assert close(g("T_matmat"), g("rmatmat").T, 1e-15)                       # the reference's own consistency
+    assert close(O.bds_dense(vals, k).numpy(), g("dense"), 1e-15)
+    assert close(O.normalize_by_blocks(vals, k).numpy(), g("normalized"), 1e-15)
+    assert close(O.congruence_bds_diag(vals, k, t(g("dvec"))).numpy(), g("congruence_diag"), 1e-14)
+    assert close(O.congruence_bds_diag(vals, k, 0.37).numpy(), g("congruence_scalar"), 1e-14)
+
+
+@pytest.mark.parametrize("family", ["rbf", "matern12", "matern32", "matern52"])
+def test_oracle_lazy_kernel_matches_reference(family):
+    g = lambda k: GX[f"lazy/{family}/{k}"]
+    ls, var = t(np.array([0.8, 1.7, 1.1])), t(1.4)
+    x1, x2 = t(g("x1")), t(g("x2"))
+    assert close(O.cross_covariance(family, x1, x2, ls, var).numpy(), g("dense"), 1e-14)
+    assert close(O.lazy_kernel_matmat(family, x1, x2, ls, var, t(g("R")), batch_size=6).numpy(), g("matmat"), 1e-13)
+    assert close(O.lazy_kernel_rmatmat(family, x1, x2, ls, var, t(g("L")), batch_size=6).numpy(), g("rmatmat"), 1e-13)
+    rows, _ = O.lazy_batch_sizes((19, 26), 8)
+    assert rows == int(g("batch_rows_1GB"))
+
+
+@pytest.mark.parametrize("tag", ["overhang", "even", "single", "per_point"])
+def test_host_layer_block_operators_match_reference(tag):
+    """The product's host-side operators that need no kernel (pure torch; they run on CPU as well) against the
+    reference's `BlockDiagonalSparse`, `_normalize_by_blocks` and the sparse x diagonal `congruence_transform`."""
+    from cagpjax_b200 import ops
+    from cagpjax_b200.linalg import congruence_transform
+    from cagpjax_b200.operators import BlockDiagonalSparse
+    from cagpjax_b200.policies.block_sparse import _normalize_by_blocks
+
+    g = lambda k: GX[f"bds/{tag}/{k}"]
+    vals, k = t(g("nz_values")), int(g("n_blocks"))
+    n = vals.shape[0]
+    op = BlockDiagonalSparse(vals, k)
+    assert close((op @ t(g("X"))).numpy(), g("matmat"), 1e-15)
+    assert close((t(g("Y")) @ op).numpy(), g("rmatmat"), 1e-14)
+    assert close((op.T @ t(g("Y")).T).numpy(), g("T_matmat"), 1e-14)
+    assert close(op.to_dense().numpy(), g("dense"), 1e-15)
+    assert close(_normalize_by_blocks(vals, k).numpy(), g("normalized"), 1e-15)
+    assert close(congruence_transform(op, ops.Diagonal(t(g("dvec")))).diag.numpy(), g("congruence_diag"), 1e-14)
+    assert close(congruence_transform(op, ops.ScalarMul(0.37, (n, n), torch.float64)).diag.numpy(), g("congruence_scalar"), 1e-14)

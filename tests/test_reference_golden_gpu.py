@@ -129,3 +129,36 @@ def test_pseudo_input_models_match_the_reference(name):
         assert err(q.mean, c["train_mean"]) < tol and err(q.variance, c["train_variance"]) < tol
         q = model.predict(st, dev(c["z"]))
         assert err(q.mean, c["test_mean"]) < tol and err(q.variance, c["test_variance"]) < tol
+
+
+@pytest.mark.parametrize("tag", ["overhang", "even", "single", "per_point"])
+def test_block_operators_match_the_reference(tag):
+    from cagpjax_b200 import ops
+    from cagpjax_b200.linalg import congruence_transform
+    from cagpjax_b200.operators import BlockDiagonalSparse
+    from cagpjax_b200.policies.block_sparse import _normalize_by_blocks
+
+    g = lambda k: GX[f"bds/{tag}/{k}"]
+    vals, k = dev(g("nz_values")), int(g("n_blocks"))
+    n = vals.shape[0]
+    op = BlockDiagonalSparse(vals, k)
+    assert err(op @ dev(g("X")), g("matmat")) < 1e-14
+    assert err(dev(g("Y")) @ op, g("rmatmat")) < 1e-14
+    assert err(op.T @ dev(g("Y")).T, g("T_matmat")) < 1e-14
+    assert err(op.to_dense(), g("dense")) < 1e-15
+    assert err(_normalize_by_blocks(vals, k), g("normalized")) < 1e-15
+    assert err(congruence_transform(op, ops.Diagonal(dev(g("dvec")))).diag, g("congruence_diag")) < 1e-14
+    assert err(congruence_transform(op, ops.ScalarMul(0.37, (n, n), torch.float64, device=DEV)).diag, g("congruence_scalar")) < 1e-14
+
+
+@pytest.mark.parametrize("family", ["rbf", "matern12", "matern32", "matern52"])
+def test_lazy_kernel_matches_the_reference(family):
+    from cagpjax_b200.operators import LazyKernel
+
+    g = lambda k: GX[f"lazy/{family}/{k}"]
+    kernel = KERNELS[family](lengthscale=dev(np.array([0.8, 1.7, 1.1])), variance=dev(1.4))
+    lk = LazyKernel(kernel, dev(g("x1")), dev(g("x2")), batch_size=6)
+    assert err(lk @ dev(g("R")), g("matmat")) < 1e-12
+    assert err(dev(g("L")) @ lk, g("rmatmat")) < 1e-12
+    assert err(lk.to_dense(), g("dense")) < 1e-13
+    assert LazyKernel(kernel, dev(g("x1")), dev(g("x2"))).batch_size_row == int(g("batch_rows_1GB"))
