@@ -1,5 +1,5 @@
 """B200KernelComputation: drop-in for cagpjax.computations.LazyKernelComputation (computations/lazy.py:15-124).
-UNRUN (no JAX in this image)."""
+Never run on JAX (none in this image); run under numpy stand-ins with emulated FFI targets: tests/test_jax_binding_wiring.py."""
 import cola
 import lineax as lx
 from cagpjax.interop import ColaLinearOperator

@@ -1,5 +1,6 @@
 """plum overload: S^T (K + sigma^2 I) S for block-sparse S and a B200LazyKernel goes to the fused projection instead
-of the dense fallback ``A.T @ (B @ A)`` (linalg/congruence.py:15-17).  UNRUN (no JAX in this image)."""
+of the dense fallback ``A.T @ (B @ A)`` (linalg/congruence.py:15-17).  Never run on JAX (none in this
+image); the overload is exercised under numpy stand-ins with emulated FFI targets: tests/test_jax_binding_wiring.py."""
 import cola
 import jax.numpy as jnp
 from cagpjax.linalg.congruence import congruence_transform

@@ -1,4 +1,5 @@
-"""FFI target registration and host-only helpers.  UNRUN (no JAX in this image); API: jax.ffi of jax >= 0.4.38."""
+"""FFI target registration and host-only helpers.  Never run on JAX (none in this image; API: jax.ffi of
+jax >= 0.4.38); registration and host helpers are exercised by tests/test_jax_binding_wiring.py under numpy stand-ins."""
 import ctypes
 import os
 

@@ -1,5 +1,6 @@
 """B200LazyKernel: the reference's LazyKernel (operators/lazy_kernel.py:11-103) with its products on the sm_100a
-kernels.  UNRUN (no JAX in this image)."""
+kernels.  Never run on JAX (none in this image); run under numpy stand-ins with emulated FFI targets
+(tests/test_jax_binding_wiring.py)."""
 import jax.numpy as jnp
 from cagpjax.operators import BlockDiagonalSparse, LazyKernel
 

@@ -1,5 +1,7 @@
 """jax.custom_vjp wrappers over the FFI targets: forward and backward kernels are paired by hand, as
-cagpjax_b200/_fused.py does with torch.autograd.Function.  UNRUN (no JAX in this image).
+cagpjax_b200/_fused.py does with torch.autograd.Function.  Never run on JAX (none in this image); the forward
+wrappers run under numpy stand-ins with emulated FFI targets (tests/test_jax_binding_wiring.py) and the reverse-mode rule
+of `project_stats` is checked there against central differences (called directly: no autodiff in the stand-ins).
 
 Layouts follow include/cagp_b200.h: xs = scaled SoA inputs (dpad, n); Mt = (K'S)^T stored k-major (k, m)."""
 import functools

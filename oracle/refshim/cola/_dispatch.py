@@ -70,6 +70,13 @@ class Function:
     def __init__(self, name):
         self.name, self.methods = name, []
 
+    def dispatch(self, fn=None, *, precedence=0):
+        """plum's `Function.dispatch`: register one more method from outside the defining module."""
+        if fn is None:
+            return lambda f: self.dispatch(f, precedence=precedence)
+        self.methods.append(Method(fn, precedence))
+        return self
+
     def __call__(self, *args, **kw):
         cands = [m for m in self.methods if m.accepts(args)]
         if not cands:

@@ -5,7 +5,7 @@ import numpy as _np
 
 import unittest as _unittest
 
-from . import lax, random, scipy, test_util  # noqa: F401
+from . import ffi, lax, random, scipy, test_util  # noqa: F401
 from . import numpy  # noqa: F401  (jax.numpy)
 
 Array = _np.ndarray
