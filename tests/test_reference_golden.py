@@ -243,3 +243,35 @@ def test_host_layer_block_operators_match_reference(tag):
     assert close(_normalize_by_blocks(vals, k).numpy(), g("normalized"), 1e-15)
     assert close(congruence_transform(op, ops.Diagonal(t(g("dvec")))).diag.numpy(), g("congruence_diag"), 1e-14)
     assert close(congruence_transform(op, ops.ScalarMul(0.37, (n, n), torch.float64)).diag.numpy(), g("congruence_scalar"), 1e-14)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mid-size cases at the benchmarked kernel shapes: tests/golden/reference_golden_mid.npz
+# (tests/golden/make_reference_golden_mid.py; 25 minutes of the reference's Python row loop, so not re-generated here)
+# ------------------------------------------------------------------------------------------------------------------
+GM = np.load(os.path.join(HERE, "golden", "reference_golden_mid.npz"))
+
+
+@pytest.mark.parametrize("name", [str(c) for c in GM["case_names"]])
+def test_oracle_matches_reference_at_benchmark_shapes(name):
+    pre = name + "/"
+    c = {k[len(pre):]: GM[k] for k in GM.files if k.startswith(pre)}
+    fam, k = str(c["family"]), int(c["n_actions"])
+    p = O.make_params(c["hp_lengthscale"], c["hp_variance"], c["hp_obs_stddev"], c["hp_mean_constant"], c["actions"])
+    st = O.cagp_init(fam, t(c["x"]), t(c["y"]), p, k)
+    assert close(st.repr_weights_proj.numpy(), c["repr_weights_proj"], 1e-9)
+    assert close(float(O.cagp_elbo(fam, st, p)), float(c["elbo"]), 1e-12)
+    assert close(float(O.cagp_prior_kl(st)), float(c["prior_kl"]), 1e-10)
+    m, v = O.cagp_predict(fam, st, p)
+    assert close(m.numpy(), c["train_mean"], 1e-11) and close(v.numpy(), c["train_variance"], 1e-11)
+    m, v = O.cagp_predict(fam, st, p, t(c["z"]))
+    assert close(m.numpy(), c["test_mean"], 1e-11) and close(v.numpy(), c["test_variance"], 1e-11)
+    es = O.elbo_structured(fam, c["x"], c["y"], c["hp_lengthscale"], float(c["hp_variance"]), float(c["hp_obs_stddev"]),
+                           float(c["hp_mean_constant"]), c["actions"], k)
+    assert close(float(es), float(c["elbo"]), 1e-11)
+    val, grads = O.elbo_and_grad_literal(fam, t(c["x"]), t(c["y"]), p, k)
+    for leaf in ("lengthscale", "variance", "obs_stddev", "mean_constant"):
+        ref = float(c["grad_" + leaf])
+        assert abs(float(grads[leaf]) - ref) <= 2e-6 * max(1.0, abs(ref)), leaf
+    ga = grads["actions"].numpy()[c["grad_actions_index"]]
+    assert np.max(np.abs(ga - c["grad_actions_sample"])) <= 2e-6 * max(1.0, np.max(np.abs(c["grad_actions_sample"])))

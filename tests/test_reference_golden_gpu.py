@@ -162,3 +162,47 @@ def test_lazy_kernel_matches_the_reference(family):
     assert err(dev(g("L")) @ lk, g("rmatmat")) < 1e-12
     assert err(lk.to_dense(), g("dense")) < 1e-13
     assert LazyKernel(kernel, dev(g("x1")), dev(g("x2"))).batch_size_row == int(g("batch_rows_1GB"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mid-size cases from the reference's own source at the benchmarked kernel shapes (reference_golden_mid.npz)
+# ------------------------------------------------------------------------------------------------------------------
+GM = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_mid.npz"))
+# expected kernel instance: level of the expanded-form fast path (csrc/ks_symx.cuh); 0 = general kernels
+EXPECTED_LEVEL = {"c3_shape_even": 1, "c3_shape_overhang": 1, "c3_shape_wide": 2, "c2_shape": 0}
+
+
+@pytest.mark.parametrize("name", [str(c) for c in GM["case_names"]])
+def test_benchmark_shapes_match_the_reference(name):
+    from cagpjax_b200 import _native as N
+
+    pre = name + "/"
+    c = {k[len(pre):]: GM[k] for k in GM.files if k.startswith(pre)}
+    fam, k, d = str(c["family"]), int(c["n_actions"]), int(c["x"].shape[1])
+    # which kernel instance this case exercises (the same scaling the model applies)
+    X, ls = dev(c["x"]), dev(c["hp_lengthscale"]).reshape(1)
+    lo, hi = torch.aminmax(X, dim=0)
+    xs = N.scale_inputs(fam, X, ls, torch.lerp(lo, hi, 0.5))
+    assert N.sym_fast_path(fam, xs, d, k, ls, N.bounding_box(xs)) == EXPECTED_LEVEL[name]
+    assert N.sym_fast_path(fam, xs, d, k, ls, N.bounding_box(xs), backward=True) == EXPECTED_LEVEL[name]
+    c["actions_kind"], c["solver"] = np.array("blocksparse"), np.array("cholesky")
+    model, data = build(c)
+    with torch.no_grad():
+        st = model.init(data)
+        assert err(st.repr_weights_proj, c["repr_weights_proj"]) < 1e-8
+        assert err(model.elbo(st), c["elbo"]) < 1e-10
+        assert err(model.prior_kl(st), c["prior_kl"]) < 1e-9
+        q = model.predict(st)
+        assert err(q.mean, c["train_mean"]) < 1e-10 and err(q.variance, c["train_variance"]) < 1e-10
+        q = model.predict(st, dev(c["z"]))
+        assert err(q.mean, c["test_mean"]) < 1e-10 and err(q.variance, c["test_variance"]) < 1e-10
+    val, grads = gpx.value_and_grad(lambda m, dd: m.elbo(m.init(dd)), model, data)
+    assert err(val, c["elbo"]) < 1e-10
+    for key, g in grads.items():
+        leaf = {"lengthscale": "lengthscale", "variance": "variance", "obs_stddev": "obs_stddev", "constant": "mean_constant",
+                "nz_values": "actions"}[key.split(".")[1]]
+        if leaf == "actions":
+            got = g.detach().cpu().numpy()[c["grad_actions_index"]]
+            assert np.max(np.abs(got - c["grad_actions_sample"])) <= 2e-6 * max(1.0, np.max(np.abs(c["grad_actions_sample"]))), key
+        else:
+            assert err(g, c["grad_" + leaf]) < 2e-6, key
