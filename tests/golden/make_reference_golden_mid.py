@@ -4,7 +4,11 @@ fast-path kernels of csrc/ks_symx.cuh, as in BASELINE config 3), with and withou
 d = 8 case with short blocks (the SPREAD shape of config 2).  Gradients of the reference's ELBO by central differences
 at a sample of action indices (all hyper-parameters).
 
-    python tests/golden/make_reference_golden_mid.py       # writes tests/golden/reference_golden_mid.npz  (~1 minute)
+    python tests/golden/make_reference_golden_mid.py       # writes tests/golden/reference_golden_mid.npz
+
+Takes ~25 minutes on 16 cores (the reference evaluates the kernel row by row through the Python-loop stand-in of
+`jax.lax.map`, and every finite-difference gradient entry costs two more ELBO evaluations), so unlike the small fixtures
+it is not re-generated inside the test suite.
 """
 import os
 import sys
