@@ -10,7 +10,8 @@ are checked
   * against the independent rectangular kernels for the full-size reverse mode (promoted from tools/c3_crosscheck.py),
     plus an oracle sample of s_bar.
 
-Parity is unpinned (oracle/cagp_oracle.py header): the oracle restates the reference, it is not the reference."""
+The oracle restates the reference, it is not the reference; what pins it against the reference's own source:
+oracle/cagp_oracle.py header and tests/test_reference_golden*.py (incl. mid-size cases at these kernel shapes)."""
 
 import numpy as np
 import pytest

@@ -1,9 +1,10 @@
 """Third-party anchors for the oracle (CPU).
 
-Parity is unpinned (the reference cannot run here, its tests hold no golden vectors), so the oracle's restated
+The third-party packages behind the reference (GPJax's kernel and likelihood formulas) cannot run here and are restated
+both in the oracle and in the stand-ins that run the reference's own source (oracle/refshim), so those restated
 formulas are additionally pinned against an INDEPENDENT published implementation that is installed in this image:
 scikit-learn's ``gaussian_process`` (kernels ``RBF`` / ``Matern(nu = 1/2, 3/2, 5/2)`` and the exact
-``GaussianProcessRegressor``).  This does not turn "unpinned" into "pinned" - scikit-learn is not the reference - but a
+``GaussianProcessRegressor``).  scikit-learn is not GPJax, so this is an independent anchor, not a pin on GPJax itself - but a
 misremembered kernel formula, a wrong ARD scaling or a wrong exact-GP limit of the CaGP posterior / ELBO in the
 oracle would show up here.
 
