@@ -9,7 +9,9 @@
 //       -I/usr/local/cuda/include -Iinclude cagpjax_b200/csrc/xla_ffi_shim.cc
 //       -Lcagpjax_b200/_lib -lcagp_b200 -o cagpjax_b200/_lib/libcagp_b200_xla.so       (one command line)
 // The Python side is jax_binding/cagpjax_b200_jax/ (custom_vjp wrappers, compute engine, congruence overload).
-// UNRUN: written against the jax >= 0.4.31 FFI headers from memory; reviewable, not verified.
+// Never built against the real header (written against the jax >= 0.4.31 FFI API from memory).  tests/test_host_logic.py
+// compiles it against a MOCK of that API (tests/mock_xla) and the real include/cagp_b200.h: syntax, every C-ABI call's
+// argument list, and handler parameters vs bindings are checked that way; the real header's details are not.
 //
 // Conventions: scalar sizes travel as int64 attributes; workspaces are extra RESULT buffers sized by the Python
 // side with the cagp_*_ws_bytes() helpers (XLA owns all memory); errors map to ffi::Error::Internal with

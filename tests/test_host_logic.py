@@ -87,6 +87,40 @@ def test_xla_ffi_shim_is_guarded_and_covers_every_compute_symbol(tmp_path):
     assert set(targets) == set(handlers) and set(targets.values()) == compute
 
 
+def test_xla_ffi_shim_compiles_against_a_mock_of_the_ffi_api(tmp_path):
+    """With tests/mock_xla on the include path the shim is NOT empty: it must compile (C++17, -Wall -Werror) against a
+    mock of xla/ffi/api/ffi.h (written from memory, so this is not a build against the real header) AND the real
+    include/cagp_b200.h.  That checks the syntax of every handler, the argument count / types of every call into the
+    C ABI, and - through the mock's static_assert - that each handler's parameters match its binding.  A deliberately
+    broken binding and a deliberately wrong C-ABI call must both fail, so the check is not vacuous."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    shim = os.path.join(ROOT, "cagpjax_b200", "csrc", "xla_ffi_shim.cc")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("CUDA headers not available")
+    base = ["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "mock_xla"), "-I" + cuda_inc,
+            "-I" + os.path.join(ROOT, "include")]
+    obj = tmp_path / "shim_mock.o"
+    subprocess.run(base + ["-c", shim, "-o", str(obj)], check=True)
+    syms = subprocess.run(["nm", str(obj)], capture_output=True, text=True).stdout
+    handlers = re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((Cagp\w+),", open(shim).read())
+    assert all(re.search(rf"\bT {h}\b", syms) for h in handlers), "every handler symbol must be exported"
+    src = open(shim).read().replace('#include "../../include/cagp_b200.h"', '#include "cagp_b200.h"')
+    broken_binding = src.replace("XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpBoundingBox, BoundingBox, CAGP_BIND() ARG RET);",
+                                 "XLA_FFI_DEFINE_HANDLER_SYMBOL(CagpBoundingBox, BoundingBox, CAGP_BIND() ARG ARG RET);")
+    broken_call = src.replace("(int32_t)k, B->untyped_data(), ws->untyped_data(),", "(int32_t)k, B->untyped_data(),", 1)
+    assert broken_binding != src and broken_call != src
+    for name, text, needle in (("binding", broken_binding, "does not match its binding"), ("call", broken_call, "error")):
+        f = tmp_path / f"broken_{name}.cc"
+        f.write_text(text)
+        res = subprocess.run(base + ["-fsyntax-only", str(f)], capture_output=True, text=True)
+        assert res.returncode != 0 and needle in res.stderr, name
+
+
 def test_jax_binding_parses_and_fails_cleanly_without_jax():
     import ast
     import glob
