@@ -87,6 +87,38 @@ def test_xla_ffi_shim_is_guarded_and_covers_every_compute_symbol(tmp_path):
     assert set(targets) == set(handlers) and set(targets.values()) == compute
 
 
+def test_jax_binding_calls_agree_with_the_shim_bindings():
+    """Every `jax.ffi.ffi_call(name, results)(operands..., attributes...)` in jax_binding/.../ops.py must pass as many
+    operands, declare as many results and name the same attributes as the handler's binding in csrc/xla_ffi_shim.cc."""
+    import ast
+
+    shim = open(os.path.join(ROOT, "cagpjax_b200", "csrc", "xla_ffi_shim.cc")).read()
+    bindings = {}
+    for m in re.finditer(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((Cagp\w+),\s*\w+,\s*(.*?)\);", shim, flags=re.S):
+        body = m.group(2)
+        attrs = re.findall(r'(?:I64|\.Attr<[^>]*(?:<[^>]*>)?[^>]*>)\("(\w+)"\)', body)
+        bindings[m.group(1)] = (len(re.findall(r"\bARG\b", body)), len(re.findall(r"\bRET\b", body)), attrs)
+    tree = ast.parse(open(os.path.join(ROOT, "jax_binding", "cagpjax_b200_jax", "ops.py")).read())
+    seen = set()
+    for node in ast.walk(tree):
+        # the call of the callable returned by jax.ffi.ffi_call(...)
+        if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Call)):
+            continue
+        inner = node.func
+        if not (isinstance(inner.func, ast.Attribute) and inner.func.attr == "ffi_call"):
+            continue
+        name = inner.args[0].value
+        spec = inner.args[1]
+        n_results = len(spec.elts) if isinstance(spec, ast.Tuple) else 1
+        n_args = len(node.args)
+        attrs = [kw.arg for kw in node.keywords]
+        assert name in bindings, name
+        assert (n_args, n_results) == bindings[name][:2], (name, n_args, n_results, bindings[name])
+        assert attrs == bindings[name][2], (name, attrs, bindings[name][2])   # XLA matches attributes by name; keep the order too
+        seen.add(name)
+    assert len(seen) >= 11, sorted(seen)   # the peer variants and the cross-covariance pair are bound from other layers
+
+
 def test_xla_ffi_shim_compiles_against_a_mock_of_the_ffi_api(tmp_path):
     """With tests/mock_xla on the include path the shim is NOT empty: it must compile (C++17, -Wall -Werror) against a
     mock of xla/ffi/api/ffi.h (written from memory, so this is not a build against the real header) AND the real
